@@ -1,0 +1,282 @@
+"""bench.py -- headline benchmark of the B200 scoring path (see the contract in DESIGN.md).
+
+A "step" is one complete exact-mode wGCL scoring run (distance tiles -> alpha grid with the
+fixed point, local 1-AUC score and global JS score).  Metric (BASELINE.json): pair-alphas per
+second = n(n+1)/2 * (#alpha values evaluated) / time, over all GPUs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+N = 1 : BASELINE.json configs[1], the reference's 10k example with --force-exact --seed 42
+        (tests/golden/example10k.npz, produced from the reference's example files).
+N > 1 : weak scaling -- a synthetic planted-partition graph with round(10000*sqrt(N)) vertices
+        (d = 32, 64 communities), i.e. the same number of pairs per GPU, its pair-matrix tiles
+        sharded over the ranks with one NCCL all-reduce of the n-length degree sums per pass.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC = "exact global+local score throughput (node-pairs x alphas / s)"
+UNIT = "pair-alphas/s"
+EMPTY = (np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int64), np.zeros(0),
+         np.zeros((0, 0)))
+
+
+def workload(n_gpus):
+    from cge_jl_b200.divergence import draw_samples
+
+    if n_gpus == 1:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "example10k.npz"))
+        edges, ew, vw, comm, emb = (z[k] for k in ("edges", "eweights", "vweights", "comm",
+                                                   "embedding"))
+        name = "CGE.jl example/10k (n=10000, m=41536, d=32, k=64) --force-exact --seed 42"
+        data = "reference example 10k graph (fixture tests/golden/example10k.npz)"
+    else:
+        from cge_jl_b200.synth import planted_partition
+
+        n = int(round(10000 * np.sqrt(n_gpus)))
+        edges, ew, vw, comm, emb = planted_partition(n, k=64, d=32, seed=1000 + n_gpus)
+        name = f"synthetic planted partition n={n} d=32 k=64, exact, --seed 42"
+        data = "synthetic"
+    n = vw.shape[0]
+    samples = draw_samples(edges, ew, n, 10000, 42, directed=False, exact=True)
+    return dict(edges=edges, ew=ew, vw=vw, comm=comm, emb=emb, n=n, samples=samples, name=name,
+                data=data)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.index)], capture_output=True, text=True, timeout=5)
+                if o.returncode == 0 and o.stdout.strip():
+                    self.rows.append([c.strip() for c in o.stdout.strip().split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({nm for r in self.rows for nm, v in zip(names, r[3:7]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def oracle_sample(w, max_alphas):
+    """The CPU port (oracle/) on a bounded prefix of the alpha grid of the same workload."""
+    import oracle
+
+    t0 = time.perf_counter()
+    _, tr = oracle.wgcl(w["edges"], w["ew"], w["comm"], w["emb"], np.zeros(w["n"]), w["vw"],
+                        samples=w["samples"], max_alphas=max_alphas)
+    dt = time.perf_counter() - t0
+    pairs = w["n"] * (w["n"] + 1) // 2
+    return pairs * tr.n_alpha_run / dt, dt, int(tr.n_alpha_run), int(sum(tr.iters))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (the line-by-line C port in oracle/; the
+    Julia original cannot run in this image) on the host cores.  The reference is single-threaded
+    (no @threads / Distributed anywhere in src/), so cores = 1."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workload(1 if args.gpus == 1 else args.gpus)
+    vals, times = [], []
+    for i in range(args.warmup + args.steps):
+        v, dt, a_run, sweeps = oracle_sample(w, args.ref_alphas)
+        if i >= args.warmup:
+            vals.append(v)
+            times.append(dt)
+    val = float(np.mean(vals))
+    sample = (f"first {args.ref_alphas} of 40 alpha values ({sweeps} fixed-point passes) of the "
+              f"same workload per step")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": w["data"], "config": {"workload": w["name"], "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from cge_jl_b200 import _lib
+    from cge_jl_b200 import divergence as dv
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the scoring path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N")
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = workload(world)
+    n = w["n"]
+    pairs = n * (n + 1) // 2
+    sc = dv.Scorer(local_rank)
+    if world > 1:
+        ids = [dv.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sc.comm_init(ids[0], rank, world)
+    problem, keep = dv.make_problem(w["edges"], w["ew"], w["comm"], w["emb"], np.zeros(n), w["vw"],
+                                    None, None, None, False, False, w["samples"], 0, args.driver)
+    h2d = sum(a.nbytes for a in keep)
+    d2h = 7 * 8
+
+    def timed(fn, count):
+        """`count` calls of fn bracketed by barrier+sync; returns max-over-ranks seconds."""
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(count):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        barrier()
+        return dt
+
+    last = {}
+
+    def step_resident():
+        last["out"], last["stats"] = sc.run()
+
+    def step_e2e():
+        sc.upload(problem, keep)
+        last["out"], last["stats"] = sc.run()
+
+    # device-resident: inputs already in HBM
+    sc.upload(problem, keep)
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev_ms, sweep_ms, sweeps, launches = [], 0.0, 0, 0
+    dt_res = 0.0
+    for _ in range(args.steps):  # one timed() per step so per-step device times can be collected
+        dt_res += timed(step_resident, 1)
+        st = last["stats"]
+        ev_ms.append(st.ms_build + st.ms_solve)
+        sweep_ms += st.ms_sweeps
+        sweeps += st.fp_sweeps
+        launches += st.launches
+    stats = last["stats"]
+    out = last["out"]
+    a_run = int(stats.n_alpha_run)
+    # end to end through the public call: host buffers, H2D + D2H inside the timed region
+    for _ in range(max(1, args.warmup // 3)):
+        step_e2e()
+    dt_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    sampler.join(timeout=2)
+    value = pairs * a_run * args.steps / dt_res
+    e2e = pairs * a_run * args.steps / dt_e2e
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_per_launch = 8.0 * pairs / world          # algorithmic: 8 B per unordered pair per pass
+    avg_launch_s = 1e-3 * sweep_ms / max(sweeps, 1)
+    achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt_res / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": w["data"],
+        "config": {"workload": w["name"], "alphas_evaluated": a_run,
+                   "fixed_point_passes": int(stats.fp_sweeps), "b_passes": int(stats.b_sweeps),
+                   "pairs": pairs, "samples_local": 10000, "tiles": int(stats.n_tiles),
+                   "l2": "inputs larger than L2 (q matrix %.0f MB per GPU vs 126 MB L2)"
+                         % (stats.matrix_bytes / 1e6),
+                   "driver": {1: "hostloop", 2: "persistent"}.get(int(stats.driver), "?"),
+                   "result": [float(x) for x in out],
+                   "device_ms_per_step": float(np.mean(ev_ms))},
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None,
+                     "kernel": "k_sweep<M,false> (fixed-point pass over the stored q matrix)",
+                     "bytes_per_launch": bytes_per_launch,
+                     "avg_launch_us": 1e6 * avg_launch_s, "launches_timed": int(sweeps),
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"
+                                    if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, a, sw = oracle_sample(w, args.ref_alphas)
+        line["cpu_baseline"] = {
+            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle/ C port of wGCL, first {a} of 40 alpha values ({sw} fixed-point "
+                      f"passes) of the same workload, {dt:.1f} s"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--driver", type=int, default=0, help="0 auto, 1 host loop, 2 persistent")
+    ap.add_argument("--ref-alphas", type=int, default=2,
+                    help="alpha values per CPU sample (bounds the CPU baseline's run time)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

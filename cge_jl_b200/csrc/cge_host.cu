@@ -1,0 +1,1186 @@
+// cge_host.cu -- C ABI (include/cge_b200.h), host driver of the alpha loop and the small
+// kernels around the pair-matrix sweeps (distance tiles, normalisation, finalize, local score).
+//
+// The control flow mirrors /root/reference/src/divergence.jl:27-257 (wGCL) and :282-561
+// (wGCL_directed); every step cites the lines it replaces.  Nothing here computes on the CPU
+// except O(m) / O(k^2) bookkeeping (C vector, degrees, star check, Jensen-Shannon over <= k^2
+// bins, early-stopping counters) -- the reference's "negligible" rows A3, A14-A16 of SURVEY.md
+// section 8(a).
+#include "../../include/cge_b200.h"
+#include "cge_kernels.cuh"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace cge {
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(e__ == cudaErrorMemoryAllocation ? CGE_B200_ERR_OOM                \
+                                                         : CGE_B200_ERR_CUDA,              \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+void launch_tiles(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a) {
+    switch ((m - 1) / 10) {
+        case 0: launch_tiles_part0(m, kind, grid, stream, a); break;
+        case 1: launch_tiles_part1(m, kind, grid, stream, a); break;
+        case 2: launch_tiles_part2(m, kind, grid, stream, a); break;
+        default: launch_tiles_part3(m, kind, grid, stream, a); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+constexpr int DK = 16;  // embedding dimensions staged per step; dp is padded to a multiple
+
+__device__ __forceinline__ void atomic_min_max_nonneg(unsigned long long *lohi, double mn,
+                                                      double mx) {
+    // non-negative doubles order like their bit patterns
+    atomicMin(lohi, (unsigned long long)__double_as_longlong(mn));
+    atomicMax(lohi + 1, (unsigned long long)__double_as_longlong(mx));
+}
+
+// Distance tiles: D_ij = sqrt(sum_c (x_ic - x_jc)^2) in difference form (auxilary.jl:14-20),
+// D_ii = distances[i] (divergence.jl:85-86; zeros for the full graph, :106-111), extrema over all
+// entries (divergence.jl:92 / :113).  STORE writes the raw tile (pads = -1), otherwise only the
+// extrema are produced (landmark mode needs nothing else of the full graph).
+template <bool STORE>
+__global__ void __launch_bounds__(NTHREADS)
+k_build_dist(const double *__restrict__ emb, int dp, const double *__restrict__ diag, int n,
+             const int2 *__restrict__ tile_ij, long long tile_begin, long long tile_end,
+             double *__restrict__ q, unsigned long long *lohi) {
+    __shared__ double sA[TILE][DK + 1];
+    __shared__ double sB[TILE][DK + 1];
+    __shared__ double s_mn[NWARPS], s_mx[NWARPS];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    double lmin = INFINITY, lmax = 0.0;
+    for (long long t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
+        const int2 ij = tile_ij[t];
+        const int bi = ij.x, bj = ij.y;
+        double acc[8][8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+        for (int k0 = 0; k0 < dp; k0 += DK) {
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = tid + NTHREADS * i, r = e >> 4, c = e & 15;
+                sA[r][c] = emb[(size_t)(bi * TILE + r) * dp + k0 + c];
+                sB[r][c] = emb[(size_t)(bj * TILE + r) * dp + k0 + c];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < DK; ++kk) {
+                double av[8], bv[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) av[i] = sA[ty + 16 * i][kk];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bv[j] = sB[tx + 16 * j][kk];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double df = av[i] - bv[j];
+                        acc[i][j] = fma(df, df, acc[i][j]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int gi = bi * TILE + ty + 16 * i;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int gj = bj * TILE + tx + 16 * j;
+                double v;
+                if (gi >= n || gj >= n) {
+                    v = -1.0;
+                } else {
+                    v = gi == gj ? (diag ? diag[gi] : 0.0) : sqrt(acc[i][j]);
+                    lmin = fmin(lmin, v);
+                    lmax = fmax(lmax, v);
+                }
+                if (STORE)
+                    q[(size_t)(t - tile_begin) * TILE_ELEMS + (size_t)(ty + 16 * i) * TILE + tx +
+                      16 * j] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lmin = fmin(lmin, __shfl_xor_sync(FULL, lmin, off));
+        lmax = fmax(lmax, __shfl_xor_sync(FULL, lmax, off));
+    }
+    if ((tid & 31) == 0) {
+        s_mn[tid >> 5] = lmin;
+        s_mx[tid >> 5] = lmax;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NWARPS; ++w) {
+            lmin = fmin(lmin, s_mn[w]);
+            lmax = fmax(lmax, s_mx[w]);
+        }
+        if (lmin <= lmax) atomic_min_max_nonneg(lohi, lmin, lmax);
+    }
+}
+
+// D -> q = ((1 - (D - lo)/(hi - lo)))^(1/4)  (divergence.jl:93 and the alpha-independent part of
+// :146); pads -> 0 so that they never contribute.
+__global__ void k_transform(double *__restrict__ q, size_t count,
+                            const unsigned long long *__restrict__ lohi) {
+    const double lo = __longlong_as_double((long long)lohi[0]);
+    const double hi = __longlong_as_double((long long)lohi[1]);
+    const double range = hi - lo;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const double x = q[i];
+        q[i] = x < 0.0 ? 0.0 : sqrt(sqrt(1.0 - (x - lo) / range));
+    }
+}
+
+__global__ void k_qdiag(const double *__restrict__ dist, int n,
+                        const unsigned long long *__restrict__ lohi, double *__restrict__ qdiag) {
+    const double lo = __longlong_as_double((long long)lohi[0]);
+    const double hi = __longlong_as_double((long long)lohi[1]);
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) qdiag[v] = sqrt(sqrt(1.0 - (dist[v] - lo) / (hi - lo)));
+}
+
+// q for the sampled pairs of the local score (divergence.jl:187-189,196-198 landmark mode with
+// the full-graph extrema, :205,210 exact mode).  Same summation order as k_build_dist.
+__global__ void k_sample_q(const double *__restrict__ emb, int dp, const int *__restrict__ ia,
+                           const int *__restrict__ ib, const double *__restrict__ diag,
+                           const unsigned long long *__restrict__ lohi, int full_graph,
+                           long long count, double *__restrict__ out) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= count) return;
+    const double lo = full_graph ? 0.0 : __longlong_as_double((long long)lohi[0]);
+    const double hi = __longlong_as_double((long long)lohi[1]);
+    const int i = ia[s], j = ib[s];
+    double dv;
+    if (i == j) {
+        dv = diag ? diag[i] : 0.0;
+    } else {
+        const double *a = emb + (size_t)i * dp, *b = emb + (size_t)j * dp;
+        double acc = 0.0;
+        for (int c = 0; c < dp; ++c) {
+            const double df = a[c] - b[c];
+            acc = fma(df, df, acc);
+        }
+        dv = sqrt(acc);
+    }
+    out[s] = sqrt(sqrt(1.0 - (dv - lo) / (hi - lo)));
+}
+
+__device__ __forceinline__ void block_max_to_slot(double e, unsigned long long *slot) {
+    __shared__ double s_max[32];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) e = fmax(e, __shfl_xor_sync(FULL, e, off));
+    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) e = fmax(e, s_max[w]);
+        atomicMax(slot, (unsigned long long)__double_as_longlong(e));
+    }
+}
+
+// sum of the per-block partials in fixed order
+__global__ void k_reduce_part(const double *__restrict__ part, int nb, int np, int n,
+                              double *__restrict__ sraw) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += __ldcg(part + (size_t)b * np + v);
+    sraw[v] = s;
+}
+
+// divergence.jl:160-166: S_i = T_i * sum, T_i += eps*T_i*(w_i/S_i - 1), diff = max|w_i - S_i|
+__global__ void k_update_u(const double *__restrict__ sraw, double *__restrict__ T,
+                           const double *__restrict__ w, int n, double eps,
+                           double *__restrict__ S, unsigned long long *slot,
+                           unsigned long long *next_slot) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (v < n) {
+        const double t = T[v];
+        const double s = t * sraw[v];
+        const double move = eps * t * (w[v] / s - 1.0);
+        T[v] = t + move;
+        S[v] = s;
+        e = fabs(w[v] - s);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_slot = 0ull;
+    block_max_to_slot(e, slot);
+}
+
+// divergence.jl:451-461 with the doubled diagonal of :442-447
+__global__ void k_update_d(const double *__restrict__ sraw_in, const double *__restrict__ sraw_out,
+                           double *__restrict__ Tin, double *__restrict__ Tout,
+                           const double *__restrict__ deg_in, const double *__restrict__ deg_out,
+                           const double *__restrict__ qdiag, int m, int n, double eps,
+                           double *__restrict__ Sin, double *__restrict__ Sout,
+                           unsigned long long *slot, unsigned long long *next_slot) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    double e = 0.0;
+    if (v < n) {
+        const double ti = Tin[v], to = Tout[v];
+        const double gd = powm_rt(qdiag[v], m);
+        const double sin = ti * (sraw_in[v] + to * gd);
+        const double sout = to * (sraw_out[v] + ti * gd);
+        Sin[v] = sin;
+        Sout[v] = sout;
+        const double di = deg_in[v], dout = deg_out[v];
+        if (di > 0.0) {
+            Tin[v] = ti + eps * ti * (di / sin - 1.0);
+            e = fmax(e, fabs(di - sin));
+        }
+        if (dout > 0.0) {
+            Tout[v] = to + eps * to * (dout / sout - 1.0);
+            e = fmax(e, fabs(dout - sout));
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_slot = 0ull;
+    block_max_to_slot(e, slot);
+}
+
+// Local score, divergence.jl:178-213 / 478-517: pos/neg = (f_a*f_b) * q^m, then
+// sum((pos > neg) * w) and sum(w).  One block, fixed reduction order.
+struct SampleSide {
+    const int *a, *b;        // scored-graph (sorted) vertex of each endpoint
+    const double *w0a, *wla; // landmark mode: init_vweights[i], vweights[v_to_l[i]] (else NULL)
+    const double *w0b, *wlb;
+    const double *q;         // (1 - D)^(1/4) of the sampled pair
+};
+
+__device__ __forceinline__ double sample_value(const SampleSide &s, long long i,
+                                               const double *Ta, const double *Tb, int m) {
+    double fa = __ldcg(Ta + s.a[i]), fb = __ldcg(Tb + s.b[i]);
+    if (s.w0a) {  // adj_T = T[l]*w0/w_l (divergence.jl:187-188)
+        fa = fa * s.w0a[i] / s.wla[i];
+        fb = fb * s.w0b[i] / s.wlb[i];
+    }
+    return fa * fb * powm_rt(s.q[i], m);
+}
+
+__global__ void __launch_bounds__(1024)
+k_auc(SampleSide pos, SampleSide neg, const double *__restrict__ wts, long long offset,
+      int K, const double *Ta, const double *Tb, int m, double *out2) {
+    __shared__ double s_num[1024], s_den[1024];
+    double num = 0.0, den = 0.0;
+    for (int s = threadIdx.x; s < K; s += blockDim.x) {
+        const long long i = offset + s;
+        const double pv = sample_value(pos, i, Ta, Tb, m);
+        const double nv = sample_value(neg, i, Ta, Tb, m);
+        const double w = wts[i];
+        num += pv > nv ? w : 0.0;
+        den += w;
+    }
+    s_num[threadIdx.x] = num;
+    s_den[threadIdx.x] = den;
+    __syncthreads();
+    for (int h = blockDim.x >> 1; h > 0; h >>= 1) {
+        if ((int)threadIdx.x < h) {
+            s_num[threadIdx.x] += s_num[threadIdx.x + h];
+            s_den[threadIdx.x] += s_den[threadIdx.x + h];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        out2[0] = s_num[0];
+        out2[1] = s_den[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CGE_B200_ERR_OOM, std::string("cudaMalloc(") + std::to_string(bytes) +
+                                              " bytes): " + cudaGetErrorString(e));
+        }
+        cap = bytes;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T *as() const {
+        return reinterpret_cast<T *>(p);
+    }
+};
+
+// NCCL is bound at run time so that single-GPU use has no NCCL dependency
+struct Id128 {  // ncclUniqueId (128 bytes, passed by value)
+    char b[128];
+};
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id128, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+    if (g_nccl.lib) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return fail(CGE_B200_ERR_NCCL, std::string("dlopen libnccl: ") + dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString =
+        (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(CGE_B200_ERR_NCCL, "libnccl lacks a required symbol");
+    return 0;
+}
+// nccl.h enum values (stable across NCCL 2.x): ncclFloat64 = 8, ncclUint64 = 5;
+// ncclSum = 0, ncclMax = 2, ncclMin = 3
+constexpr int kNcclF64 = 8, kNcclU64 = 5, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3;
+
+static inline int64_t tile_index(int64_t nb, int64_t bi, int64_t bj) {
+    return bi * nb - bi * (bi - 1) / 2 + (bj - bi);
+}
+
+static void shard_range(int64_t n_tiles, int rank, int n_ranks, int64_t *b, int64_t *e) {
+    // contiguous, near-equal tile counts (every tile costs the same 128 KB read)
+    *b = n_tiles * rank / n_ranks;
+    *e = n_tiles * (rank + 1) / n_ranks;
+}
+
+// Jensen-Shannon with the +1 prior (auxilary.jl:34-52) over the bins listed in `bins`
+static double js_bins(const std::vector<double> &C, const std::vector<double> &B,
+                      const std::vector<int64_t> &bins, const std::vector<uint8_t> &is_int,
+                      int use_mask, int internal) {
+    double sp1 = 0.0, sp2 = 0.0;
+    int64_t cnt = 0;
+    for (size_t t = 0; t < bins.size(); ++t) {
+        if (use_mask && (is_int[t] != 0) != (internal != 0)) continue;
+        sp1 += C[bins[t]];
+        sp2 += B[bins[t]];
+        ++cnt;
+    }
+    sp1 += (double)cnt;
+    sp2 += (double)cnt;
+    double f = 0.0;
+    for (size_t t = 0; t < bins.size(); ++t) {
+        if (use_mask && (is_int[t] != 0) != (internal != 0)) continue;
+        const double p = (C[bins[t]] + 1.0) / sp1, q = (B[bins[t]] + 1.0) / sp2;
+        const double mm = (p + q) / 2.0;
+        f += p * std::log(p / mm) + q * std::log(q / mm);
+    }
+    return f / 2.0;
+}
+
+}  // namespace cge
+
+using namespace cge;
+
+struct cge_b200_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    bool uploaded = false;
+    // problem
+    bool directed = false, split = false, landmark = false, star = false;
+    int64_t n = 0, np = 0, nb = 0, d = 0, dp = 0, k = 0, K = 0, n_sets = 1;
+    int64_t n_full = 0, npf = 0, nbf = 0;
+    int max_alphas = CGE_B200_N_ALPHA, driver = CGE_B200_DRIVER_HOSTLOOP;
+    int64_t n_tiles = 0, tile_begin = 0, tile_end = 0, n_tiles_full = 0;
+    // multi-rank
+    int rank = 0, n_ranks = 1;
+    void *nccl_comm = nullptr;
+    // host copies
+    std::vector<int64_t> perm;           // sorted position -> caller's 0-based vertex
+    std::vector<double> C;               // k*k observed community mass (divergence.jl:55-63/337-345)
+    std::vector<int64_t> bins;           // bins of C/B that enter JS, in the reference's order
+    std::vector<uint8_t> bin_internal;   // vect_I (divergence.jl:66-71 / 348-351)
+    // device
+    DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
+        sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out;
+    DevBuf s_pda, s_pdb, s_nda, s_ndb, s_pa, s_pb, s_na, s_nb, s_pw, s_pw0a, s_pwla, s_pw0b, s_pwlb, s_nw0a, s_nwla, s_nw0b,
+        s_nwlb, s_pq, s_nq;
+    float ms_upload = 0.f;
+    int64_t launches = 0;
+    std::vector<cudaEvent_t> evpool;  // pairs of events around every sweep launch
+    size_t ev_used = 0;
+    std::vector<uint8_t> ev_is_b;
+    cudaEvent_t next_event() {
+        if (ev_used == evpool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            evpool.push_back(e);
+        }
+        return evpool[ev_used++];
+    }
+};
+
+namespace cge {
+
+static int upload_vec(DevBuf &buf, const void *src, size_t bytes, cudaStream_t st) {
+    if (int rc = buf.ensure(std::max<size_t>(bytes, 16))) return rc;
+    if (bytes) CUDA_TRY(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+static std::vector<int2> make_tile_table(int64_t nb) {
+    std::vector<int2> t;
+    t.reserve((size_t)(nb * (nb + 1) / 2));
+    for (int bi = 0; bi < nb; ++bi)
+        for (int bj = bi; bj < nb; ++bj) t.push_back(make_int2(bi, bj));
+    return t;
+}
+
+static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
+    auto t0 = std::chrono::steady_clock::now();
+    if (!p || p->struct_size != (int32_t)sizeof(cge_b200_problem))
+        return fail(CGE_B200_ERR_ARG, "cge_b200_problem.struct_size mismatch");
+    if (p->index_base != 0 && p->index_base != 1) return fail(CGE_B200_ERR_ARG, "index_base");
+    if (p->m <= 0 || !p->edge_src || !p->edge_dst || !p->eweights || !p->comm || !p->embed ||
+        !p->distances || !p->vweights || p->d <= 0)
+        return fail(CGE_B200_ERR_ARG, "missing input array");
+    const int64_t base = p->index_base;
+    h->uploaded = false;
+    h->directed = p->directed != 0;
+    h->split = p->split != 0;
+    h->landmark = p->n_full > 0;
+    h->max_alphas = p->max_alphas > 0 ? std::min<int>(p->max_alphas, CGE_B200_N_ALPHA)
+                                      : CGE_B200_N_ALPHA;
+    h->driver = p->driver == CGE_B200_DRIVER_AUTO ? CGE_B200_DRIVER_HOSTLOOP : p->driver;
+    // no_vertices = maximum(edges) (divergence.jl:41 / :294)
+    int64_t n = 0;
+    for (int64_t e = 0; e < p->m; ++e) {
+        n = std::max(n, std::max(p->edge_src[e], p->edge_dst[e]) - base + 1);
+        if (p->edge_src[e] < base || p->edge_dst[e] < base)
+            return fail(CGE_B200_ERR_ARG, "edge endpoint below index_base");
+    }
+    if (p->n_comm != n)
+        return fail(CGE_B200_ERR_ASSERT_COMM, "No. communities not matching no. vertices");
+    if (p->n_distances != n)
+        return fail(CGE_B200_ERR_ASSERT_DIST,
+                    "Distances vector length is not equal to no. vertices");
+    if (p->embed_rows < n) return fail(CGE_B200_ERR_ARG, "embedding has fewer rows than vertices");
+    if (n >= (int64_t)1 << 30) return fail(CGE_B200_ERR_ARG, "too many vertices");
+    h->n = n;
+    h->d = p->d;
+    h->dp = (p->d + DK - 1) / DK * DK;
+    h->nb = (n + TILE - 1) / TILE;
+    h->np = h->nb * TILE;
+    h->K = p->n_samples;
+    h->n_sets = p->n_samples > 0 ? std::max<int64_t>(p->n_sets, 1) : 1;
+    h->n_full = p->n_full;
+    // communities, 0-based; n_parts = maximum(comm) (divergence.jl:51)
+    int64_t k = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (p->comm[i] < base) return fail(CGE_B200_ERR_ARG, "community id below index_base");
+        k = std::max(k, p->comm[i] - base + 1);
+    }
+    h->k = k;
+    // sort vertices by community (stable): row/column community of a tile changes rarely
+    h->perm.resize((size_t)n);
+    std::iota(h->perm.begin(), h->perm.end(), 0);
+    std::stable_sort(h->perm.begin(), h->perm.end(),
+                     [&](int64_t a, int64_t b) { return p->comm[a] < p->comm[b]; });
+    std::vector<int64_t> inv((size_t)n);
+    for (int64_t s = 0; s < n; ++s) inv[(size_t)h->perm[(size_t)s]] = s;
+
+    // C vector (divergence.jl:55-63 undirected: bin (min c, max c); :337-345 directed: (c_src, c_dst))
+    h->C.assign((size_t)(k * k), 0.0);
+    std::vector<double> deg_in, deg_out;
+    if (h->directed) {
+        deg_in.assign((size_t)n, 0.0);
+        deg_out.assign((size_t)n, 0.0);
+    }
+    std::vector<int64_t> star((size_t)(h->directed ? n : 0), 0);
+    for (int64_t e = 0; e < p->m; ++e) {
+        const int64_t u = p->edge_src[e] - base, v = p->edge_dst[e] - base;
+        const int64_t cu = p->comm[u] - base, cv = p->comm[v] - base;
+        if (h->directed) {
+            h->C[(size_t)(cu * k + cv)] += p->eweights[e];
+            deg_out[(size_t)u] += p->eweights[e];  // divergence.jl:311-319
+            deg_in[(size_t)v] += p->eweights[e];
+            star[(size_t)u] += 1;
+            star[(size_t)v] += 1;
+        } else {
+            h->C[(size_t)(std::min(cu, cv) * k + std::max(cu, cv))] += p->eweights[e];
+        }
+    }
+    h->star = false;
+    if (h->directed) {  // divergence.jl:322-334
+        bool has_nm1 = false, has_2nm1 = false;
+        int64_t sum = 0, cnt2 = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            has_nm1 |= star[(size_t)i] == n - 1;
+            has_2nm1 |= star[(size_t)i] == 2 * (n - 1);
+            cnt2 += star[(size_t)i] == 2;
+            sum += star[(size_t)i];
+        }
+        if (has_nm1 && sum == 2 * (n - 1)) h->star = true;
+        else if (has_2nm1 && cnt2 == n - 1) h->star = true;
+    }
+    h->bins.clear();
+    h->bin_internal.clear();
+    if (h->directed) {
+        for (int64_t a = 0; a < k; ++a)
+            for (int64_t b = 0; b < k; ++b) {
+                h->bins.push_back(a * k + b);
+                h->bin_internal.push_back(a == b);
+            }
+    } else {
+        for (int64_t a = 0; a < k; ++a)
+            for (int64_t b = a; b < k; ++b) {
+                h->bins.push_back(a * k + b);
+                h->bin_internal.push_back(a == b);
+            }
+    }
+    if (h->star) {
+        h->uploaded = true;
+        return 0;
+    }
+
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t np = h->np, dp = h->dp;
+    // sorted + padded per-vertex arrays
+    std::vector<double> emb((size_t)(np * dp), 0.0), dist((size_t)np, 0.0), w((size_t)np, 1.0),
+        w2, Ta((size_t)np, 0.0), Tb;
+    std::vector<int> comm((size_t)np, -1);
+    for (int64_t s = 0; s < n; ++s) {
+        const int64_t v = h->perm[(size_t)s];
+        for (int64_t c = 0; c < p->d; ++c)
+            emb[(size_t)(s * dp + c)] = p->embed[v * p->embed_row_stride + c * p->embed_col_stride];
+        dist[(size_t)s] = p->distances[v];
+        comm[(size_t)s] = (int)(p->comm[v] - base);
+    }
+    if (h->directed) {  // Tin/Tout = 1, 0 where the degree is 0 (divergence.jl:399-402)
+        w.assign((size_t)np, 0.0);
+        w2.assign((size_t)np, 0.0);
+        Tb.assign((size_t)np, 0.0);
+        for (int64_t s = 0; s < n; ++s) {
+            const int64_t v = h->perm[(size_t)s];
+            w[(size_t)s] = deg_in[(size_t)v];
+            w2[(size_t)s] = deg_out[(size_t)v];
+            Ta[(size_t)s] = deg_in[(size_t)v] == 0.0 ? 0.0 : 1.0;
+            Tb[(size_t)s] = deg_out[(size_t)v] == 0.0 ? 0.0 : 1.0;
+        }
+    } else {  // T = ones (divergence.jl:118)
+        for (int64_t s = 0; s < n; ++s) {
+            w[(size_t)s] = p->vweights[h->perm[(size_t)s]];
+            Ta[(size_t)s] = 1.0;
+        }
+    }
+    int rc;
+    if ((rc = upload_vec(h->emb, emb.data(), emb.size() * 8, st))) return rc;
+    if ((rc = upload_vec(h->dist, dist.data(), dist.size() * 8, st))) return rc;
+    if ((rc = upload_vec(h->w, w.data(), w.size() * 8, st))) return rc;
+    if ((rc = upload_vec(h->T0a, Ta.data(), Ta.size() * 8, st))) return rc;
+    if ((rc = upload_vec(h->comm, comm.data(), comm.size() * 4, st))) return rc;
+    if (h->directed) {
+        if ((rc = upload_vec(h->w2, w2.data(), w2.size() * 8, st))) return rc;
+        if ((rc = upload_vec(h->T0b, Tb.data(), Tb.size() * 8, st))) return rc;
+    }
+    // tile table and this rank's share
+    h->n_tiles = h->nb * (h->nb + 1) / 2;
+    shard_range(h->n_tiles, h->rank, h->n_ranks, &h->tile_begin, &h->tile_end);
+    {
+        std::vector<int2> tij = make_tile_table(h->nb);
+        if ((rc = upload_vec(h->tile_ij, tij.data(), tij.size() * sizeof(int2), st))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));  // tij is a local
+    }
+    const size_t local_tiles = (size_t)(h->tile_end - h->tile_begin);
+    if ((rc = h->q.ensure(std::max<size_t>(local_tiles, 1) * TILE_ELEMS * 8))) return rc;
+    const size_t part_bytes = (size_t)h->nb * (size_t)np * 8;
+    if ((rc = h->partA.ensure(part_bytes))) return rc;
+    if (h->directed && (rc = h->partB.ensure(part_bytes))) return rc;
+    for (DevBuf *b : {&h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->qdiag})
+        if ((rc = b->ensure((size_t)np * 8))) return rc;
+    if ((rc = h->B.ensure(std::max<size_t>((size_t)(k * k) * 8, 16)))) return rc;
+    if ((rc = h->lohi.ensure(64))) return rc;
+    if ((rc = h->slots.ensure(64))) return rc;
+    if ((rc = h->auc_out.ensure(64))) return rc;
+
+    // landmark mode: original graph arrays for the local score
+    if (h->landmark && h->K > 0) {
+        if (!p->init_vweights || !p->v_to_l || !p->init_embed)
+            return fail(CGE_B200_ERR_ARG, "landmark mode needs init_vweights, v_to_l, init_embed");
+        h->nbf = (h->n_full + TILE - 1) / TILE;
+        h->npf = h->nbf * TILE;
+        h->n_tiles_full = h->nbf * (h->nbf + 1) / 2;
+        std::vector<double> ef((size_t)(h->npf * dp), 0.0);
+        for (int64_t v = 0; v < h->n_full; ++v)
+            for (int64_t c = 0; c < p->d; ++c)
+                ef[(size_t)(v * dp + c)] =
+                    p->init_embed[v * p->init_row_stride + c * p->init_col_stride];
+        if ((rc = upload_vec(h->emb_full, ef.data(), ef.size() * 8, st))) return rc;
+        std::vector<int2> tij = make_tile_table(h->nbf);
+        if ((rc = upload_vec(h->tile_ij_full, tij.data(), tij.size() * sizeof(int2), st)))
+            return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    // sampled pairs: (da,db) = vertices whose embedding rows give the distance (original graph in
+    // landmark mode), (ta,tb) = sorted scored-graph vertices whose T enters (divergence.jl:187-189)
+    if (h->K > 0) {
+        if (!p->pos_i || !p->pos_j || !p->pos_w || !p->neg_i || !p->neg_j)
+            return fail(CGE_B200_ERR_ARG, "n_samples > 0 but sample arrays missing");
+        const int64_t S = h->K * h->n_sets;
+        const int64_t lim = h->landmark ? h->n_full : n;
+        auto side = [&](const int64_t *si, const int64_t *sj, DevBuf &d_da, DevBuf &d_db,
+                        DevBuf &d_ta, DevBuf &d_tb, DevBuf &w0a, DevBuf &wla, DevBuf &w0b,
+                        DevBuf &wlb) -> int {
+            std::vector<int> da((size_t)S), db((size_t)S), ta((size_t)S), tb2((size_t)S);
+            std::vector<double> v0a, vla, v0b, vlb;
+            if (h->landmark) {
+                v0a.resize((size_t)S); vla.resize((size_t)S);
+                v0b.resize((size_t)S); vlb.resize((size_t)S);
+            }
+            for (int64_t s = 0; s < S; ++s) {
+                int64_t i = si[s] - base, j = sj[s] - base;
+                if (i < 0 || j < 0 || i >= lim || j >= lim)
+                    return fail(CGE_B200_ERR_ARG, "sampled vertex id out of range");
+                // undirected pairs are addressed as (min,max) (divergence.jl:133; idx needs i<=j)
+                if (!h->directed && i > j) std::swap(i, j);
+                if (h->landmark) {
+                    const int64_t li = p->v_to_l[i] - base, lj = p->v_to_l[j] - base;
+                    if (li < 0 || lj < 0 || li >= n || lj >= n)
+                        return fail(CGE_B200_ERR_ARG, "v_to_l out of range");
+                    da[(size_t)s] = (int)i;
+                    db[(size_t)s] = (int)j;
+                    ta[(size_t)s] = (int)inv[(size_t)li];
+                    tb2[(size_t)s] = (int)inv[(size_t)lj];
+                    v0a[(size_t)s] = p->init_vweights[i];
+                    vla[(size_t)s] = p->vweights[li];
+                    v0b[(size_t)s] = p->init_vweights[j];
+                    vlb[(size_t)s] = p->vweights[lj];
+                } else {
+                    da[(size_t)s] = ta[(size_t)s] = (int)inv[(size_t)i];
+                    db[(size_t)s] = tb2[(size_t)s] = (int)inv[(size_t)j];
+                }
+            }
+            int r;
+            if ((r = upload_vec(d_da, da.data(), da.size() * 4, st))) return r;
+            if ((r = upload_vec(d_db, db.data(), db.size() * 4, st))) return r;
+            if ((r = upload_vec(d_ta, ta.data(), ta.size() * 4, st))) return r;
+            if ((r = upload_vec(d_tb, tb2.data(), tb2.size() * 4, st))) return r;
+            if (h->landmark) {
+                if ((r = upload_vec(w0a, v0a.data(), v0a.size() * 8, st))) return r;
+                if ((r = upload_vec(wla, vla.data(), vla.size() * 8, st))) return r;
+                if ((r = upload_vec(w0b, v0b.data(), v0b.size() * 8, st))) return r;
+                if ((r = upload_vec(wlb, vlb.data(), vlb.size() * 8, st))) return r;
+            }
+            CUDA_TRY(cudaStreamSynchronize(st));  // the vectors are locals
+            return 0;
+        };
+        if ((rc = side(p->pos_i, p->pos_j, h->s_pda, h->s_pdb, h->s_pa, h->s_pb, h->s_pw0a,
+                       h->s_pwla, h->s_pw0b, h->s_pwlb)))
+            return rc;
+        if ((rc = side(p->neg_i, p->neg_j, h->s_nda, h->s_ndb, h->s_na, h->s_nb, h->s_nw0a,
+                       h->s_nwla, h->s_nw0b, h->s_nwlb)))
+            return rc;
+        if ((rc = upload_vec(h->s_pw, p->pos_w, (size_t)S * 8, st))) return rc;
+        if ((rc = h->s_pq.ensure((size_t)S * 8))) return rc;
+        if ((rc = h->s_nq.ensure((size_t)S * 8))) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h->uploaded = true;
+    h->ms_upload =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return 0;
+}
+
+static int nccl_check(int rc, const char *what) {
+    if (rc == 0) return 0;
+    return fail(CGE_B200_ERR_NCCL, std::string(what) + ": " +
+                                       (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+}
+
+static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_stats *stats) {
+    if (!h->uploaded) return fail(CGE_B200_ERR_STATE, "run() before upload()");
+    auto wall0 = std::chrono::steady_clock::now();
+    const double inf = std::numeric_limits<double>::infinity();
+    cge_b200_stats st_local;
+    cge_b200_stats &S = stats ? *stats : st_local;
+    std::memset(&S, 0, sizeof(S));
+    S.struct_size = (int32_t)sizeof(cge_b200_stats);
+    for (int a = 0; a < CGE_B200_N_ALPHA; ++a) S.div[a] = S.auc[a] = NAN;
+    S.n = h->n;
+    S.n_pairs = h->n * (h->n + 1) / 2;
+    S.n_ranks = h->n_ranks;
+    S.driver = h->driver;
+    S.ms_upload = h->ms_upload;
+    if (h->star) {  // divergence.jl:332-334
+        out[0] = -1.0;
+        for (int i = 1; i < 6; ++i) out[i] = 0.0;
+        *out_len = 6;
+        return 0;
+    }
+    *out_len = 7;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->launches = 0;
+    h->ev_used = 0;
+    h->ev_is_b.clear();
+    const int n = (int)h->n, np = (int)h->np, nb = (int)h->nb, dp = (int)h->dp, k = (int)h->k;
+    const long long tb = h->tile_begin, te = h->tile_end;
+    const int local_tiles = (int)(te - tb);
+    const int grid = std::max(1, std::min(local_tiles, 2 * h->sm_count));
+    S.n_tiles = (int)h->n_tiles;
+    S.grid = grid;
+    S.matrix_bytes = (int64_t)local_tiles * TILE_ELEMS * 8;
+    cudaEvent_t ev0, ev1, ev2;
+    CUDA_TRY(cudaEventCreate(&ev0));
+    CUDA_TRY(cudaEventCreate(&ev1));
+    CUDA_TRY(cudaEventCreate(&ev2));
+    CUDA_TRY(cudaEventRecord(ev0, st));
+
+    // ---- distances, extrema, q (divergence.jl:79-93 / 359-375) ----
+    unsigned long long *lohi = h->lohi.as<unsigned long long>();  // [0..1] scored graph, [2..3] full
+    {
+        const double pinf = inf;
+        unsigned long long init[4];
+        std::memcpy(&init[0], &pinf, 8);
+        init[1] = 0ull;
+        init[2] = init[0];
+        init[3] = 0ull;
+        CUDA_TRY(cudaMemcpyAsync(lohi, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    }
+    if (local_tiles > 0) {
+        k_build_dist<true><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp, h->dist.as<double>(),
+                                                      n, h->tile_ij.as<int2>(), tb, te,
+                                                      h->q.as<double>(), lohi);
+        ++h->launches;
+    }
+    if (h->n_ranks > 1) {
+        if (int rc = nccl_check(g_nccl.AllReduce(lohi, lohi, 1, kNcclU64, kNcclMin, h->nccl_comm, st),
+                                "ncclAllReduce(min)"))
+            return rc;
+        if (int rc = nccl_check(
+                g_nccl.AllReduce(lohi + 1, lohi + 1, 1, kNcclU64, kNcclMax, h->nccl_comm, st),
+                "ncclAllReduce(max)"))
+            return rc;
+    }
+    if (local_tiles > 0) {
+        k_transform<<<4 * h->sm_count, 256, 0, st>>>(h->q.as<double>(),
+                                                     (size_t)local_tiles * TILE_ELEMS, lohi);
+        ++h->launches;
+    }
+    k_qdiag<<<(n + 255) / 256, 256, 0, st>>>(h->dist.as<double>(), n, lohi, h->qdiag.as<double>());
+    ++h->launches;
+    // ---- landmark mode: extrema of the full graph (divergence.jl:104-115 / 386-397) ----
+    const long long SK = h->K * h->n_sets;
+    if (h->K > 0) {
+        if (h->landmark) {
+            const int gridf = (int)std::max<int64_t>(
+                1, std::min<int64_t>(h->n_tiles_full, (int64_t)2 * h->sm_count));
+            k_build_dist<false><<<gridf, NTHREADS, 0, st>>>(
+                h->emb_full.as<double>(), dp, nullptr, (int)h->n_full, h->tile_ij_full.as<int2>(),
+                0, h->n_tiles_full, nullptr, lohi + 2);
+            ++h->launches;
+        }
+        const double *e = h->landmark ? h->emb_full.as<double>() : h->emb.as<double>();
+        const double *dg = h->landmark ? nullptr : h->dist.as<double>();
+        const unsigned long long *lh = h->landmark ? lohi + 2 : lohi;
+        const int blocks = (int)((SK + 255) / 256);
+        k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh,
+                                           h->landmark, SK, h->s_pq.as<double>());
+        k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_nda.as<int>(), h->s_ndb.as<int>(), dg, lh,
+                                           h->landmark, SK, h->s_nq.as<double>());
+        h->launches += 2;
+    }
+    // ---- T (divergence.jl:118 / 399-402), partial slots ----
+    CUDA_TRY(cudaMemcpyAsync(h->Ta.p, h->T0a.p, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
+    if (h->directed)
+        CUDA_TRY(cudaMemcpyAsync(h->Tb.p, h->T0b.p, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemsetAsync(h->partA.p, 0, (size_t)nb * np * 8, st));
+    if (h->directed) CUDA_TRY(cudaMemsetAsync(h->partB.p, 0, (size_t)nb * np * 8, st));
+    CUDA_TRY(cudaMemsetAsync(h->slots.p, 0, 64, st));
+    CUDA_TRY(cudaEventRecord(ev1, st));
+
+    SweepArgs A;
+    A.q = h->q.as<double>();
+    A.tile_ij = h->tile_ij.as<int2>();
+    A.tile_begin = tb;
+    A.tile_end = te;
+    A.nb = nb; A.np = np; A.n = n; A.k = k;
+    A.Ta = h->Ta.as<double>();
+    A.Tb = h->Tb.as<double>();
+    A.partA = h->partA.as<double>();
+    A.partB = h->partB.as<double>();
+    A.comm = h->comm.as<int>();
+    A.B = h->B.as<double>();
+
+    SampleSide sp, sn;
+    if (h->K > 0) {
+        sp.a = h->s_pa.as<int>(); sp.b = h->s_pb.as<int>();
+        sn.a = h->s_na.as<int>(); sn.b = h->s_nb.as<int>();
+        sp.q = h->s_pq.as<double>(); sn.q = h->s_nq.as<double>();
+        if (h->landmark) {
+            sp.w0a = h->s_pw0a.as<double>(); sp.wla = h->s_pwla.as<double>();
+            sp.w0b = h->s_pw0b.as<double>(); sp.wlb = h->s_pwlb.as<double>();
+            sn.w0a = h->s_nw0a.as<double>(); sn.wla = h->s_nwla.as<double>();
+            sn.w0b = h->s_nw0b.as<double>(); sn.wlb = h->s_nwlb.as<double>();
+        } else {
+            sp.w0a = sp.wla = sp.w0b = sp.wlb = nullptr;
+            sn.w0a = sn.wla = sn.w0b = sn.wlb = nullptr;
+        }
+    }
+
+    // ---- alpha loop (divergence.jl:139-254 / 423-558) ----
+    const double delta = 0.001;
+    int alpha_div_counter = 5, alpha_auc_counter = 5;
+    bool skip_div = false, skip_auc = h->K <= 0;
+    double best_div = inf, best_div_ext = inf, best_div_int = inf, best_auc_err = inf,
+           best_auc = inf, best_alpha = -1.0, best_alpha_auc = -1.0;
+    unsigned long long *slots = h->slots.as<unsigned long long>();
+    std::vector<double> Bh((size_t)k * k);
+    const int ublocks = (n + 255) / 256;
+    long long sweep_no = 0;
+    for (int m = 1; m <= h->max_alphas; ++m) {
+        const double alpha = 0.25 * m;
+        double diff = 1.0, eps = h->directed ? 0.9 : 0.25;  // :150,:34 / :434-435
+        int it = 0;
+        while (diff > delta) {  // :151 / :436
+            if (local_tiles > 0) {
+                cudaEventRecord(h->next_event(), st);
+                launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
+                cudaEventRecord(h->next_event(), st);
+                h->ev_is_b.push_back(0);
+                ++h->launches;
+            }
+            k_reduce_part<<<ublocks, 256, 0, st>>>(A.partA, nb, np, n, h->sraw_a.as<double>());
+            ++h->launches;
+            if (h->directed) {
+                k_reduce_part<<<ublocks, 256, 0, st>>>(A.partB, nb, np, n, h->sraw_b.as<double>());
+                ++h->launches;
+            }
+            if (h->n_ranks > 1) {
+                if (int rc = nccl_check(g_nccl.AllReduce(h->sraw_a.p, h->sraw_a.p, (size_t)n,
+                                                         kNcclF64, kNcclSum, h->nccl_comm, st),
+                                        "ncclAllReduce(S)"))
+                    return rc;
+                if (h->directed)
+                    if (int rc = nccl_check(g_nccl.AllReduce(h->sraw_b.p, h->sraw_b.p, (size_t)n,
+                                                             kNcclF64, kNcclSum, h->nccl_comm, st),
+                                            "ncclAllReduce(Sout)"))
+                        return rc;
+            }
+            unsigned long long *slot = slots + (sweep_no & 1), *next = slots + ((sweep_no + 1) & 1);
+            if (h->directed)
+                k_update_d<<<ublocks, 256, 0, st>>>(
+                    h->sraw_a.as<double>(), h->sraw_b.as<double>(), h->Ta.as<double>(),
+                    h->Tb.as<double>(), h->w.as<double>(), h->w2.as<double>(),
+                    h->qdiag.as<double>(), m, n, eps, h->Sa.as<double>(), h->Sb.as<double>(), slot,
+                    next);
+            else
+                k_update_u<<<ublocks, 256, 0, st>>>(h->sraw_a.as<double>(), h->Ta.as<double>(),
+                                                    h->w.as<double>(), n, eps, h->Sa.as<double>(),
+                                                    slot, next);
+            ++h->launches;
+            unsigned long long bits = 0;
+            CUDA_TRY(cudaMemcpyAsync(&bits, slot, 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            double f;
+            std::memcpy(&f, &bits, 8);
+            if (h->directed && f > diff) eps *= 0.99;  // :462-464
+            diff = f;
+            ++it;
+            ++sweep_no;
+            ++S.fp_sweeps;
+            if (it >= 200000)
+                return fail(CGE_B200_ERR_STATE, "fixed point did not converge in 200000 passes");
+        }
+        S.iters[m - 1] = it;
+        S.n_alpha_run = m;
+        // ---- local score (divergence.jl:178-224 / 478-528) ----
+        if (!skip_auc) {
+            const long long off = (h->n_sets > 1 ? (long long)(m - 1) : 0) * h->K;
+            // undirected: T_a*T_b; directed: Tout of the source, Tin of the target (:488-490,:507)
+            const double *fa = h->directed ? h->Tb.as<double>() : h->Ta.as<double>();
+            const double *fb = h->Ta.as<double>();
+            k_auc<<<1, 1024, 0, st>>>(sp, sn, h->s_pw.as<double>(), off, (int)h->K, fa, fb, m,
+                                      h->auc_out.as<double>());
+            ++h->launches;
+            double r2[2];
+            CUDA_TRY(cudaMemcpyAsync(r2, h->auc_out.p, 16, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const double auc = 1.0 - r2[0] / r2[1];  // :213
+            S.auc[m - 1] = auc;
+            if (auc < best_auc) {  // :215-223
+                best_auc = auc;
+                best_auc_err = 1.96 * std::sqrt(auc * (1.0 - auc) / (double)h->K);
+                best_alpha_auc = alpha;
+                alpha_auc_counter = 5;
+            } else {
+                alpha_auc_counter -= 1;
+                skip_auc = alpha_auc_counter == 0;
+            }
+        }
+        // ---- global score (divergence.jl:226-252 / 530-556) ----
+        if (!skip_div) {
+            CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
+            if (local_tiles > 0) {
+                cudaEventRecord(h->next_event(), st);
+                launch_tiles(m, h->directed ? 3 : 2, grid, st, A);
+                cudaEventRecord(h->next_event(), st);
+                h->ev_is_b.push_back(1);
+                ++h->launches;
+            }
+            ++S.b_sweeps;
+            if (h->n_ranks > 1)
+                if (int rc = nccl_check(g_nccl.AllReduce(h->B.p, h->B.p, (size_t)k * k, kNcclF64,
+                                                         kNcclSum, h->nccl_comm, st),
+                                        "ncclAllReduce(B)"))
+                    return rc;
+            CUDA_TRY(cudaMemcpyAsync(Bh.data(), h->B.p, (size_t)k * k * 8, cudaMemcpyDeviceToHost,
+                                     st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            double f, div_int = 0.0, div_ext = 0.0;
+            if (!h->split) {
+                f = js_bins(h->C, Bh, h->bins, h->bin_internal, 0, 1);
+            } else {
+                div_int = js_bins(h->C, Bh, h->bins, h->bin_internal, 1, 1);
+                div_ext = js_bins(h->C, Bh, h->bins, h->bin_internal, 1, 0);
+                f = (div_int + div_ext) / 2.0;
+            }
+            S.div[m - 1] = f;
+            if (f < best_div) {  // :242-251
+                best_div = f;
+                best_alpha = alpha;
+                best_div_ext = !h->split ? 0.0 : div_ext;
+                best_div_int = !h->split ? 0.0 : div_int;
+                alpha_div_counter = 5;
+            } else {
+                alpha_div_counter -= 1;
+                skip_div = alpha_div_counter == 0;
+            }
+        }
+        if (skip_div && skip_auc) break;  // :253
+    }
+    CUDA_TRY(cudaEventRecord(ev2, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventElapsedTime(&S.ms_build, ev0, ev1));
+    CUDA_TRY(cudaEventElapsedTime(&S.ms_solve, ev1, ev2));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    cudaEventDestroy(ev2);
+    for (size_t i = 0; i < h->ev_is_b.size(); ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->evpool[2 * i], h->evpool[2 * i + 1]) == cudaSuccess)
+            (h->ev_is_b[i] ? S.ms_bsweeps : S.ms_sweeps) += ms;
+    }
+    {
+        unsigned long long lh[4];
+        CUDA_TRY(cudaMemcpy(lh, lohi, sizeof(lh), cudaMemcpyDeviceToHost));
+        std::memcpy(&S.lo, &lh[0], 8);
+        std::memcpy(&S.hi, &lh[1], 8);
+        std::memcpy(&S.hi_full, &lh[3], 8);
+    }
+    out[0] = best_alpha; out[1] = best_div; out[2] = best_div_ext; out[3] = best_div_int;
+    out[4] = best_alpha_auc; out[5] = best_auc; out[6] = best_auc_err;  // :256
+    S.launches = h->launches;
+    S.ms_total =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return 0;
+}
+
+}  // namespace cge
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+void cge_b200_version(int *major, int *minor, int *patch) {
+    if (major) *major = CGE_B200_VERSION_MAJOR;
+    if (minor) *minor = CGE_B200_VERSION_MINOR;
+    if (patch) *patch = CGE_B200_VERSION_PATCH;
+}
+
+int cge_b200_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return c;
+}
+
+const char *cge_b200_last_error(void) { return g_err.c_str(); }
+
+int cge_b200_create(int device, cge_b200_handle **out) {
+    if (!out) return fail(CGE_B200_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int c = cge_b200_device_count();
+    if (c <= 0) return fail(CGE_B200_ERR_CUDA, "no CUDA device is usable (there is no CPU fallback)");
+    if (device < 0 || device >= c) return fail(CGE_B200_ERR_ARG, "device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    cge_b200_handle *h = new cge_b200_handle();
+    h->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(CGE_B200_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = h;
+    return 0;
+}
+
+void cge_b200_destroy(cge_b200_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+    for (DevBuf *b :
+         {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
+          &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
+          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
+          &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
+          &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})
+        b->release();
+    for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int cge_b200_upload(cge_b200_handle *h, const cge_b200_problem *p) {
+    if (!h) return fail(CGE_B200_ERR_ARG, "handle is NULL");
+    return do_upload(h, p);
+}
+
+int cge_b200_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_stats *stats) {
+    if (!h || !out || !out_len) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    if (stats && stats->struct_size != 0 && stats->struct_size != (int32_t)sizeof(cge_b200_stats))
+        return fail(CGE_B200_ERR_ARG, "cge_b200_stats.struct_size mismatch");
+    return do_run(h, out, out_len, stats);
+}
+
+int cge_b200_score(const cge_b200_problem *p, double *out, int32_t *out_len,
+                   cge_b200_stats *stats) {
+    if (!p || !out || !out_len) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    cge_b200_handle *h = nullptr;
+    int rc = cge_b200_create(0, &h);
+    if (rc) return rc;
+    rc = cge_b200_upload(h, p);
+    if (!rc) rc = cge_b200_run(h, out, out_len, stats);
+    cge_b200_destroy(h);
+    return rc;
+}
+
+int cge_b200_comm_id_size(void) { return (int)sizeof(Id128); }
+
+int cge_b200_comm_unique_id(void *id_bytes) {
+    if (!id_bytes) return fail(CGE_B200_ERR_ARG, "id_bytes is NULL");
+    if (int rc = nccl_load()) return rc;
+    return nccl_check(g_nccl.GetUniqueId(id_bytes), "ncclGetUniqueId");
+}
+
+int cge_b200_comm_init(cge_b200_handle *h, const void *id_bytes, int rank, int n_ranks) {
+    if (!h || !id_bytes || n_ranks < 1 || rank < 0 || rank >= n_ranks)
+        return fail(CGE_B200_ERR_ARG, "bad comm_init argument");
+    if (n_ranks == 1) {
+        h->rank = 0;
+        h->n_ranks = 1;
+        return 0;
+    }
+    if (int rc = nccl_load()) return rc;
+    CUDA_TRY(cudaSetDevice(h->device));
+    Id128 id;
+    std::memcpy(&id, id_bytes, sizeof(id));
+    if (int rc = nccl_check(g_nccl.CommInitRank(&h->nccl_comm, n_ranks, id, rank),
+                            "ncclCommInitRank"))
+        return rc;
+    h->rank = rank;
+    h->n_ranks = n_ranks;
+    h->uploaded = false;
+    return 0;
+}
+
+int cge_b200_shard_plan(int64_t n, int rank, int n_ranks, int64_t *n_tiles, int64_t *tile_begin,
+                        int64_t *tile_end) {
+    if (n <= 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !n_tiles || !tile_begin ||
+        !tile_end)
+        return fail(CGE_B200_ERR_ARG, "bad shard_plan argument");
+    const int64_t nb = (n + TILE - 1) / TILE;
+    *n_tiles = nb * (nb + 1) / 2;
+    shard_range(*n_tiles, rank, n_ranks, tile_begin, tile_end);
+    return 0;
+}
+
+int cge_b200_debug_read(cge_b200_handle *h, int what, double *buf, int64_t n_elems) {
+    if (!h || !buf) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    if (!h->uploaded || h->star) return fail(CGE_B200_ERR_STATE, "nothing uploaded");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    const int64_t n = h->n;
+    if (what == 0) {
+        if (n_elems < n * n) return fail(CGE_B200_ERR_ARG, "buffer too small");
+        if (h->n_ranks != 1) return fail(CGE_B200_ERR_STATE, "dense read needs all tiles local");
+        std::vector<double> tile((size_t)TILE_ELEMS);
+        for (int64_t bi = 0; bi < h->nb; ++bi)
+            for (int64_t bj = bi; bj < h->nb; ++bj) {
+                const int64_t t = tile_index(h->nb, bi, bj);
+                CUDA_TRY(cudaMemcpy(tile.data(), h->q.as<double>() + (size_t)t * TILE_ELEMS,
+                                    (size_t)TILE_ELEMS * 8, cudaMemcpyDeviceToHost));
+                for (int r = 0; r < TILE; ++r)
+                    for (int c = 0; c < TILE; ++c) {
+                        const int64_t si = bi * TILE + r, sj = bj * TILE + c;
+                        if (si >= n || sj >= n) continue;
+                        const int64_t vi = h->perm[(size_t)si], vj = h->perm[(size_t)sj];
+                        buf[vi * n + vj] = tile[(size_t)r * TILE + c];
+                        if (bi != bj) buf[vj * n + vi] = tile[(size_t)r * TILE + c];
+                    }
+            }
+        return 0;
+    }
+    const DevBuf *src = what == 1 ? &h->Ta : what == 2 ? &h->Tb : what == 3 ? &h->Sa
+                        : what == 4 ? &h->Sb : nullptr;
+    if (!src || !src->p) return fail(CGE_B200_ERR_ARG, "unknown or unavailable probe");
+    if (n_elems < n) return fail(CGE_B200_ERR_ARG, "buffer too small");
+    std::vector<double> tmp((size_t)n);
+    CUDA_TRY(cudaMemcpy(tmp.data(), src->p, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    for (int64_t s = 0; s < n; ++s) buf[h->perm[(size_t)s]] = tmp[(size_t)s];
+    return 0;
+}
+
+}  // extern "C"

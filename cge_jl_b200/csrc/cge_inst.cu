@@ -1,0 +1,41 @@
+// cge_inst.cu -- instantiates the tile kernels for ten exponents per translation unit
+// (compiled four times with -DCGE_PART=0..3 so the 160 instantiations build in parallel).
+#include "cge_kernels.cuh"
+
+#ifndef CGE_PART
+#error "compile with -DCGE_PART=0..3"
+#endif
+
+namespace cge {
+
+#define CGE_CASE(MM)                                                         \
+    case MM:                                                                 \
+        switch (kind) {                                                      \
+            case 0: k_sweep<MM, false><<<grid, NTHREADS, 0, stream>>>(a); break;  \
+            case 1: k_sweep<MM, true><<<grid, NTHREADS, 0, stream>>>(a); break;   \
+            case 2: k_bsweep<MM, false><<<grid, NTHREADS, 0, stream>>>(a); break; \
+            default: k_bsweep<MM, true><<<grid, NTHREADS, 0, stream>>>(a); break; \
+        }                                                                    \
+        break;
+
+#define CGE_CAT_(a, b) a##b
+#define CGE_CAT(a, b) CGE_CAT_(a, b)
+
+void CGE_CAT(launch_tiles_part, CGE_PART)(int m, int kind, int grid, cudaStream_t stream,
+                                          const SweepArgs &a) {
+    switch (m) {
+        CGE_CASE(CGE_PART * 10 + 1)
+        CGE_CASE(CGE_PART * 10 + 2)
+        CGE_CASE(CGE_PART * 10 + 3)
+        CGE_CASE(CGE_PART * 10 + 4)
+        CGE_CASE(CGE_PART * 10 + 5)
+        CGE_CASE(CGE_PART * 10 + 6)
+        CGE_CASE(CGE_PART * 10 + 7)
+        CGE_CASE(CGE_PART * 10 + 8)
+        CGE_CASE(CGE_PART * 10 + 9)
+        CGE_CASE(CGE_PART * 10 + 10)
+        default: break;
+    }
+}
+
+}  // namespace cge

@@ -1,0 +1,373 @@
+// cge_kernels.cuh -- device code of the stored-regime pair-matrix sweeps (sm_100a).
+//
+// Data layout (DESIGN.md "Layout in HBM"): vertices are sorted by community and padded to
+// np = nb*128; the symmetric matrix q_ij = (1 - D_ij)^(1/4) is stored as the upper-triangular
+// sequence of 128x128 FP64 tiles (bi <= bj, row-major inside a tile, diagonal tiles stored as
+// full symmetric squares, pad entries 0).  Because alpha = m/4, the geometric kernel of
+// divergence.jl:142-148 is (1-D)^alpha = q^m, evaluated on the fly with <= 8 multiplies, so one
+// pass over the matrix moves 8 bytes per unordered pair.
+//
+// One pass (divergence.jl:152-159) = every tile (bi,bj) produces
+//     row partials  sum_c T_c q_rc^m  -> part[bj][bi*128 + r]
+//     col partials  sum_r T_r q_rc^m  -> part[bi][bj*128 + c]      (bi != bj)
+// Each slot part[b][v] is written by exactly one tile, so the reduction over b done by the
+// finalize kernel has a fixed order (bit-reproducible, no atomics).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cge {
+
+constexpr int TILE = 128;
+constexpr int TILE_ELEMS = TILE * TILE;
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+constexpr int ROWS_PER_WARP = TILE / NWARPS;  // 16
+constexpr unsigned FULL = 0xffffffffu;
+
+struct SweepArgs {
+    const double *q;       // this rank's tiles: global tile t at q + (t - tile_begin) * TILE_ELEMS
+    const int2 *tile_ij;   // [n_tiles] (bi, bj) of every global tile
+    long long tile_begin, tile_end;
+    int nb, np, n, k;
+    const double *Ta;      // undirected: T        directed: Tin
+    const double *Tb;      //                      directed: Tout
+    double *partA;         // [nb][np] undirected: S partials   directed: Sin partials
+    double *partB;         //                                   directed: Sout partials
+    const int *comm;       // [np] community per (sorted) vertex, -1 on pads
+    double *B;             // [k][k] expected community mass (divergence.jl:228-234 / 532-538)
+};
+
+// q^M with a fixed multiplication chain (binary powering), M = 4*alpha in 1..40
+template <int M>
+__device__ __forceinline__ double powm(double q) {
+    if constexpr (M == 1) {
+        return q;
+    } else if constexpr (M % 2 == 0) {
+        const double h = powm<M / 2>(q);
+        return h * h;
+    } else {
+        return powm<M - 1>(q) * q;
+    }
+}
+
+__device__ __forceinline__ double powm_rt(double q, int m) {
+    double r = 1.0, b = q;
+    while (m) {
+        if (m & 1) r *= b;
+        b *= b;
+        m >>= 1;
+    }
+    return r;
+}
+
+// streaming 16-byte load of matrix data: read once per pass, keep it out of L1
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(p));
+    return v;
+}
+
+// Reduce NV per-lane values across the 32 lanes of a warp with NV-1 + (5 - log2 NV) shuffle
+// steps instead of 5*NV.  On return v[0] holds the warp total of value index
+// treduce_index<NV>(lane); the summation tree is fixed.
+template <int NV0, int NV, int OFF>
+struct TReduce {
+    static __device__ __forceinline__ void run(double (&v)[NV0], int lane) {
+        if constexpr (OFF >= 1) {
+            if constexpr (NV > 1) {
+                constexpr int H = NV / 2;
+                const bool up = (lane & OFF) != 0;
+#pragma unroll
+                for (int i = 0; i < H; ++i) {
+                    const double send = up ? v[i] : v[i + H];
+                    const double keep = up ? v[i + H] : v[i];
+                    v[i] = keep + __shfl_xor_sync(FULL, send, OFF);
+                }
+                TReduce<NV0, H, OFF / 2>::run(v, lane);
+            } else {
+                v[0] += __shfl_xor_sync(FULL, v[0], OFF);
+                TReduce<NV0, 1, OFF / 2>::run(v, lane);
+            }
+        }
+    }
+};
+template <int NV>
+__device__ __forceinline__ void warp_treduce(double (&v)[NV], int lane) {
+    TReduce<NV, NV, 16>::run(v, lane);
+}
+template <int NV>
+__device__ __forceinline__ int treduce_index(int lane) {
+    // NV = 16 -> lane >> 1, NV = 8 -> lane >> 2
+    return NV == 16 ? (lane >> 1) : NV == 8 ? (lane >> 2) : NV == 4 ? (lane >> 3) : (lane >> 4);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-point pass, undirected (divergence.jl:152-159)
+// warp w owns rows 16w..16w+15 of the tile, lane l owns columns 2l, 2l+1, 64+2l, 65+2l
+// ---------------------------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int bi, int bj,
+                                            const SweepArgs &a, double *s_col) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row0 = w * ROWS_PER_WARP;
+    const double *Tc = a.Ta + (size_t)bj * TILE;
+    const double2 tc01 = __ldcg(reinterpret_cast<const double2 *>(Tc) + lane);
+    const double2 tc23 = __ldcg(reinterpret_cast<const double2 *>(Tc + 64) + lane);
+    const double trow =
+        lane < ROWS_PER_WARP ? __ldcg(a.Ta + (size_t)bi * TILE + row0 + lane) : 0.0;
+    const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
+    double racc[ROWS_PER_WARP];
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#pragma unroll
+    for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
+        const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane);
+        const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane);
+        const double ti = __shfl_sync(FULL, trow, rr);
+        const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
+        const double g2 = powm<M>(v23.x), g3 = powm<M>(v23.y);
+        racc[rr] = fma(g3, tc23.y, fma(g2, tc23.x, fma(g1, tc01.y, g0 * tc01.x)));
+        c0 = fma(ti, g0, c0);
+        c1 = fma(ti, g1, c1);
+        c2 = fma(ti, g2, c2);
+        c3 = fma(ti, g3, c3);
+    }
+    warp_treduce<ROWS_PER_WARP>(racc, lane);
+    if ((lane & 1) == 0)
+        a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + treduce_index<16>(lane)] = racc[0];
+    const bool offdiag = bi != bj;
+    if (offdiag) {
+        double2 *sc = reinterpret_cast<double2 *>(s_col + w * TILE);
+        sc[lane] = make_double2(c0, c1);
+        sc[32 + lane] = make_double2(c2, c3);
+    }
+    __syncthreads();
+    if (offdiag && threadIdx.x < TILE) {
+        double s = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARPS; ++w2) s += s_col[w2 * TILE + threadIdx.x];
+        a.partA[(size_t)bi * a.np + (size_t)bj * TILE + threadIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fixed-point pass, directed (divergence.jl:437-449)
+//   Sin_i  += Tin_i * Tout_j * g     Sin_j  += Tin_j * Tout_i * g
+//   Sout_i += Tin_j * Tout_i * g     Sout_j += Tin_i * Tout_j * g
+// partA collects the Sin sums without their own Tin factor, partB the Sout sums without Tout.
+// The second copy of the diagonal term (i == j is added twice at :444-447) is added by the
+// finalize kernel.
+// ---------------------------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int bi, int bj,
+                                            const SweepArgs &a, double *s_col) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row0 = w * ROWS_PER_WARP;
+    const double *Tic = a.Ta + (size_t)bj * TILE, *Toc = a.Tb + (size_t)bj * TILE;
+    const double2 ti01 = __ldcg(reinterpret_cast<const double2 *>(Tic) + lane);
+    const double2 ti23 = __ldcg(reinterpret_cast<const double2 *>(Tic + 64) + lane);
+    const double2 to01 = __ldcg(reinterpret_cast<const double2 *>(Toc) + lane);
+    const double2 to23 = __ldcg(reinterpret_cast<const double2 *>(Toc + 64) + lane);
+    const bool ld = lane < ROWS_PER_WARP;
+    const double trow_in = ld ? __ldcg(a.Ta + (size_t)bi * TILE + row0 + lane) : 0.0;
+    const double trow_out = ld ? __ldcg(a.Tb + (size_t)bi * TILE + row0 + lane) : 0.0;
+    const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
+    double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0;  // Sin column sums  (Tout_r * g)
+    double co0 = 0.0, co1 = 0.0, co2 = 0.0, co3 = 0.0;  // Sout column sums (Tin_r * g)
+#pragma unroll
+    for (int batch = 0; batch < 2; ++batch) {
+        double rin[8], rout[8];
+#pragma unroll
+        for (int r8 = 0; r8 < 8; ++r8) {
+            const int rr = batch * 8 + r8;
+            const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane);
+            const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane);
+            const double t_in = __shfl_sync(FULL, trow_in, rr);
+            const double t_out = __shfl_sync(FULL, trow_out, rr);
+            const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
+            const double g2 = powm<M>(v23.x), g3 = powm<M>(v23.y);
+            rin[r8] = fma(g3, to23.y, fma(g2, to23.x, fma(g1, to01.y, g0 * to01.x)));
+            rout[r8] = fma(g3, ti23.y, fma(g2, ti23.x, fma(g1, ti01.y, g0 * ti01.x)));
+            ci0 = fma(t_out, g0, ci0);
+            ci1 = fma(t_out, g1, ci1);
+            ci2 = fma(t_out, g2, ci2);
+            ci3 = fma(t_out, g3, ci3);
+            co0 = fma(t_in, g0, co0);
+            co1 = fma(t_in, g1, co1);
+            co2 = fma(t_in, g2, co2);
+            co3 = fma(t_in, g3, co3);
+        }
+        warp_treduce<8>(rin, lane);
+        warp_treduce<8>(rout, lane);
+        if ((lane & 3) == 0) {
+            const size_t o = (size_t)bj * a.np + (size_t)bi * TILE + row0 + batch * 8 +
+                             treduce_index<8>(lane);
+            a.partA[o] = rin[0];
+            a.partB[o] = rout[0];
+        }
+    }
+    const bool offdiag = bi != bj;
+    if (offdiag) {
+        double2 *sa = reinterpret_cast<double2 *>(s_col + w * TILE);
+        double2 *sb = reinterpret_cast<double2 *>(s_col + NWARPS * TILE + w * TILE);
+        sa[lane] = make_double2(ci0, ci1);
+        sa[32 + lane] = make_double2(ci2, ci3);
+        sb[lane] = make_double2(co0, co1);
+        sb[32 + lane] = make_double2(co2, co3);
+    }
+    __syncthreads();
+    if (offdiag) {
+        const int c = threadIdx.x & (TILE - 1);
+        const double *src = s_col + (threadIdx.x >> 7) * NWARPS * TILE;
+        double s = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARPS; ++w2) s += src[w2 * TILE + c];
+        double *dst = (threadIdx.x >> 7) ? a.partB : a.partA;
+        dst[(size_t)bi * a.np + (size_t)bj * TILE + c] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// expected community mass B (divergence.jl:228-234 undirected, 532-538 directed).
+// Vertices are sorted by community, so along the 16 rows of a warp the row community changes
+// rarely: column accumulators are flushed (warp-reduced per column community, one FP64 atomic
+// per bin) only when it does.  B does not feed back into the fixed point, so the atomics'
+// summation order only perturbs the score at the 1e-16 level.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void flush_bins(double v, int bin_col, long long bin_base,
+                                           long long col_stride, double *B, int lane) {
+    // v: this lane's contribution for community bin_col (or -1 on pads)
+    const int b0 = __shfl_sync(FULL, bin_col, 0);
+    if (__all_sync(FULL, bin_col == b0)) {
+        if (b0 >= 0) {
+            const double s = warp_sum(v);
+            if (lane == 0) atomicAdd(B + bin_base + (long long)b0 * col_stride, s);
+        }
+    } else if (bin_col >= 0 && v != 0.0) {
+        atomicAdd(B + bin_base + (long long)bin_col * col_stride, v);
+    }
+}
+
+template <int M, bool DIRECTED>
+__device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi, int bj,
+                                           const SweepArgs &a) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int row0 = w * ROWS_PER_WARP;
+    const int gc0 = bj * TILE + 2 * lane, gc2 = bj * TILE + 64 + 2 * lane;
+    const int2 cc01 = __ldcg(reinterpret_cast<const int2 *>(a.comm + gc0));
+    const int2 cc23 = __ldcg(reinterpret_cast<const int2 *>(a.comm + gc2));
+    const int cc[4] = {cc01.x, cc01.y, cc23.x, cc23.y};
+    const int gc[4] = {gc0, gc0 + 1, gc2, gc2 + 1};
+    // column factors: undirected T_c; directed Tin_c (for B[cr][cc]) and Tout_c (for B[cc][cr])
+    const double2 ta01 = __ldcg(reinterpret_cast<const double2 *>(a.Ta + gc0));
+    const double2 ta23 = __ldcg(reinterpret_cast<const double2 *>(a.Ta + gc2));
+    const double tca[4] = {ta01.x, ta01.y, ta23.x, ta23.y};
+    double tcb[4] = {0.0, 0.0, 0.0, 0.0};
+    if (DIRECTED) {
+        const double2 tb01 = __ldcg(reinterpret_cast<const double2 *>(a.Tb + gc0));
+        const double2 tb23 = __ldcg(reinterpret_cast<const double2 *>(a.Tb + gc2));
+        tcb[0] = tb01.x; tcb[1] = tb01.y; tcb[2] = tb23.x; tcb[3] = tb23.y;
+    }
+    const bool ld = lane < ROWS_PER_WARP;
+    const int grow = bi * TILE + row0 + lane;
+    const int crow = ld ? __ldcg(a.comm + grow) : -1;
+    // row factors: undirected T_r; directed Tout_r (rowA) and Tin_r (rowB)
+    const double trow_a = ld ? __ldcg((DIRECTED ? a.Tb : a.Ta) + grow) : 0.0;
+    const double trow_b = (DIRECTED && ld) ? __ldcg(a.Ta + grow) : 0.0;
+    const bool diag = bi == bj;
+    const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
+    double accA[4] = {0.0, 0.0, 0.0, 0.0}, accB[4] = {0.0, 0.0, 0.0, 0.0};
+    int cur = __shfl_sync(FULL, crow, 0);
+
+    auto flush = [&](int cr) {
+        if (cr >= 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                // B[cr][cc] += (sum_r rowA_r g) * colA_c
+                flush_bins(accA[k] * tca[k], cc[k], (long long)cr * a.k, 1, a.B, lane);
+                if (DIRECTED && !diag)  // B[cc][cr] += (sum_r Tin_r g) * Tout_c
+                    flush_bins(accB[k] * tcb[k], cc[k], (long long)cr, a.k, a.B, lane);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) accA[k] = accB[k] = 0.0;
+    };
+
+#pragma unroll
+    for (int batch = 0; batch < 4; ++batch) {
+        double2 v01[4], v23[4];
+#pragma unroll
+        for (int r8 = 0; r8 < 4; ++r8) {
+            v01[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + lane);
+            v23[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + 32 + lane);
+        }
+#pragma unroll
+        for (int r8 = 0; r8 < 4; ++r8) {
+            const int rr = batch * 4 + r8;
+            const int cr = __shfl_sync(FULL, crow, rr);
+            if (cr != cur) {  // warp-uniform
+                flush(cur);
+                cur = cr;
+            }
+            double g[4] = {powm<M>(v01[r8].x), powm<M>(v01[r8].y), powm<M>(v23[r8].x),
+                           powm<M>(v23[r8].y)};
+            if (!DIRECTED && diag) {  // unordered pairs once: keep col >= row (divergence.jl:229-230)
+                const int gr = bi * TILE + row0 + rr;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[k] = gc[k] >= gr ? g[k] : 0.0;
+            }
+            const double ra = __shfl_sync(FULL, trow_a, rr);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) accA[k] = fma(ra, g[k], accA[k]);
+            if (DIRECTED) {
+                const double rb = __shfl_sync(FULL, trow_b, rr);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) accB[k] = fma(rb, g[k], accB[k]);
+            }
+        }
+    }
+    flush(cur);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels: grid-stride over this rank's tiles
+// ---------------------------------------------------------------------------------------------
+template <int M, bool DIRECTED>
+__global__ void __launch_bounds__(NTHREADS, 2) k_sweep(const __grid_constant__ SweepArgs a) {
+    __shared__ __align__(16) double s_col[2][(DIRECTED ? 2 : 1) * NWARPS * TILE];
+    int it = 0;
+    for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++it) {
+        const int2 ij = a.tile_ij[t];
+        const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
+        if (DIRECTED)
+            tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[it & 1]);
+        else
+            tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[it & 1]);
+    }
+}
+
+template <int M, bool DIRECTED>
+__global__ void __launch_bounds__(NTHREADS, 2) k_bsweep(const __grid_constant__ SweepArgs a) {
+    for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x) {
+        const int2 ij = a.tile_ij[t];
+        tile_bpass<M, DIRECTED>(a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS, ij.x, ij.y, a);
+    }
+}
+
+// host-side dispatch over the compile-time exponent; defined in cge_inst_*.cu
+// kind: 0 = sweep undirected, 1 = sweep directed, 2 = B undirected, 3 = B directed
+void launch_tiles(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part0(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part1(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part2(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part3(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+
+}  // namespace cge

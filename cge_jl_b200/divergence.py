@@ -1,0 +1,281 @@
+"""``wGCL`` / ``wGCL_directed`` with the reference's signatures, running on the B200.
+
+Mirror of the Julia entry points (/root/reference/src/divergence.jl:27-31, 282-286): same
+positional arguments (1-based ids, as ``parseargs`` / ``landmarks`` produce them), same 7-element
+return vector (6 for the directed star-graph exit), same assertion messages, same progress dots
+on stderr.  What stays on the host is what SURVEY.md section 8(b) leaves in the Julia wrapper:
+building E / NE and drawing the sampled pairs for the local score (divergence.jl:121-137,
+184-210, 484-513).  Everything else happens inside ``libcge_b200.so`` through the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+
+import numpy as np
+
+from . import _lib
+
+N_ALPHA = _lib.N_ALPHA
+_ASSERTS = {
+    _lib.ERR_ASSERT_COMM: "No. communities not matching no. vertices",
+    _lib.ERR_ASSERT_DIST: "Distances vector length is not equal to no. vertices",
+}
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
+
+
+def _pi(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64)) if a is not None else None
+
+
+# ---------------------------------------------------------------------------------------------
+# sampling (host side of the boundary)
+# ---------------------------------------------------------------------------------------------
+def _sample_non_edges(rng, n, codes_sorted, K, directed):
+    """K pairs drawn uniformly with replacement from NE (divergence.jl:121-137 / 405-421):
+    unordered i<j (ordered i!=j when directed) that are not in the edge set.  The reference
+    materialises NE and indexes it; rejection sampling draws from the same distribution without
+    the O(n^2) array."""
+    out_i = np.empty(K, dtype=np.int64)
+    out_j = np.empty(K, dtype=np.int64)
+    got = 0
+    while got < K:
+        need = max(2 * (K - got), 64)
+        i = rng.integers(1, n + 1, size=need)
+        j = rng.integers(1, n + 1, size=need)
+        if not directed:
+            i, j = np.minimum(i, j), np.maximum(i, j)
+        ok = i != j
+        code = i * (n + 1) + j
+        pos = np.searchsorted(codes_sorted, code)
+        pos[pos >= codes_sorted.shape[0]] = 0
+        ok &= codes_sorted[pos] != code if codes_sorted.size else True
+        i, j = i[ok][: K - got], j[ok][: K - got]
+        out_i[got: got + i.shape[0]] = i
+        out_j[got: got + i.shape[0]] = j
+        got += i.shape[0]
+    return out_i, out_j
+
+
+def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact):
+    """Draw the positive / negative pairs of the local score where the reference draws them.
+
+    Returns ``(pos_i, pos_j, pos_w, neg_i, neg_j)`` with shape ``(n_sets, K)``, 1-based ids of
+    the original graph.  ``seed != -1`` reseeds before every draw, so every alpha sees the same
+    sets (n_sets = 1, divergence.jl:184,193,202,209); ``seed == -1`` draws fresh sets per alpha
+    (n_sets = 40).  In directed exact mode the positive pairs come from a second, unseeded
+    continuation draw while the weights stay those of the first (the overwrite at
+    divergence.jl:505-510).  NumPy's generator replaces Julia's RNG stream: the sets are
+    identically distributed, not identical.
+    """
+    adj_edges = _i64(adj_edges)
+    w = _f64(adj_eweights)
+    m = adj_edges.shape[0]
+    if directed:
+        e_i, e_j = adj_edges[:, 0], adj_edges[:, 1]
+    else:
+        e_i, e_j = adj_edges.min(axis=1), adj_edges.max(axis=1)  # divergence.jl:133
+    codes = np.unique(e_i * (adj_n + 1) + e_j)
+    n_sets = 1 if seed != -1 else N_ALPHA
+    pi = np.empty((n_sets, K), dtype=np.int64)
+    pj = np.empty_like(pi)
+    ni = np.empty_like(pi)
+    nj = np.empty_like(pi)
+    pw = np.empty((n_sets, K))
+    free_rng = np.random.default_rng()
+    for s in range(n_sets):
+        rng = np.random.default_rng(seed) if seed != -1 else free_rng
+        idx = rng.integers(0, m, size=K)
+        pw[s] = w[idx]
+        if directed and exact:
+            idx = rng.integers(0, m, size=K)  # second draw, no reseed (divergence.jl:510)
+        pi[s], pj[s] = e_i[idx], e_j[idx]
+        rng = np.random.default_rng(seed) if seed != -1 else free_rng
+        ni[s], nj[s] = _sample_non_edges(rng, adj_n, codes, K, directed)
+    return pi, pj, pw, ni, nj
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI call
+# ---------------------------------------------------------------------------------------------
+class Scorer:
+    """Thin RAII wrapper over a ``cge_b200_handle`` (device buffers persist between calls)."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._lib.cge_b200_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"cge_b200_create failed ({rc}): {_lib.last_error()}")
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.cge_b200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def comm_init(self, id_bytes, rank, n_ranks):
+        buf = C.create_string_buffer(bytes(id_bytes), len(id_bytes))
+        rc = self._lib.cge_b200_comm_init(self._h, C.cast(buf, C.c_void_p), rank, n_ranks)
+        _check(rc)
+
+    def upload(self, problem, keep):
+        self._keep = keep
+        _check(self._lib.cge_b200_upload(self._h, C.byref(problem)))
+
+    def run(self):
+        out = np.zeros(7)
+        n_out = C.c_int32(7)
+        stats = _lib.Stats()
+        _check(self._lib.cge_b200_run(self._h, _pd(out), C.byref(n_out), C.byref(stats)))
+        return out[: n_out.value].copy(), stats
+
+    def debug_read(self, what, n):
+        size = n * n if what == 0 else n
+        buf = np.zeros(size)
+        _check(self._lib.cge_b200_debug_read(self._h, what, _pd(buf), size))
+        return buf.reshape(n, n) if what == 0 else buf
+
+
+def unique_id():
+    lib = _lib.load()
+    buf = C.create_string_buffer(lib.cge_b200_comm_id_size())
+    _check(lib.cge_b200_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return buf.raw
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    if rc in _ASSERTS:
+        raise AssertionError(_ASSERTS[rc])
+    if rc == _lib.ERR_OOM:
+        raise MemoryError(_lib.last_error())
+    raise RuntimeError(f"libcge_b200 error {rc}: {_lib.last_error()}")
+
+
+def make_problem(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
+                 init_embed, split, directed, samples, max_alphas=0, driver=0):
+    """Fill a ``cge_b200_problem`` from reference-style (1-based) arrays.
+
+    Returns ``(problem, keep)``; ``keep`` holds the arrays the struct points into.
+    """
+    edges = _i64(edges)
+    src, dst = _i64(edges[:, 0]), _i64(edges[:, 1])
+    ew = _f64(eweights)
+    cm = _i64(np.asarray(comm).reshape(-1))
+    em = np.asarray(embed, dtype=np.float64)
+    if em.ndim != 2:
+        raise ValueError("embed must be a matrix")
+    di, vw = _f64(distances), _f64(vweights)
+    p = _lib.Problem()
+    p.struct_size = C.sizeof(_lib.Problem)
+    p.index_base = 1
+    p.directed, p.split = int(bool(directed)), int(bool(split))
+    p.m, p.edge_src, p.edge_dst, p.eweights = src.shape[0], _pi(src), _pi(dst), _pd(ew)
+    p.n_comm, p.comm = cm.shape[0], _pi(cm)
+    p.embed, p.embed_rows, p.d = _pd(em), em.shape[0], em.shape[1]
+    p.embed_row_stride, p.embed_col_stride = em.strides[0] // 8, em.strides[1] // 8
+    p.n_distances, p.distances, p.vweights = di.shape[0], _pd(di), _pd(vw)
+    keep = [src, dst, ew, cm, em, di, vw]
+    n_full = 0 if v_to_l is None else len(v_to_l)
+    if n_full:
+        ivw, v2l = _f64(init_vweights), _i64(v_to_l)
+        iem = np.asarray(init_embed, dtype=np.float64)
+        p.n_full, p.init_vweights, p.v_to_l, p.init_embed = n_full, _pd(ivw), _pi(v2l), _pd(iem)
+        p.init_row_stride, p.init_col_stride = iem.strides[0] // 8, iem.strides[1] // 8
+        keep += [ivw, v2l, iem]
+    if samples is not None:
+        pi, pj, pw, ni, nj = samples
+        pi, pj, ni, nj = (np.atleast_2d(_i64(x)) for x in (pi, pj, ni, nj))
+        pw = np.atleast_2d(_f64(pw))
+        p.n_sets, p.n_samples = pi.shape
+        p.pos_i, p.pos_j, p.pos_w, p.neg_i, p.neg_j = _pi(pi), _pi(pj), _pd(pw), _pi(ni), _pi(nj)
+        keep += [pi, pj, pw, ni, nj]
+    p.max_alphas, p.driver = int(max_alphas), int(driver)
+    return p, keep
+
+
+def _score(directed, edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
+           init_edges, init_eweights, init_embed, split, seed, auc_samples, verbose, samples,
+           return_stats, max_alphas, driver, scorer):
+    edges = _i64(edges)
+    no_vertices = int(edges.max())                      # divergence.jl:41
+    no_edges = edges.shape[0]
+    if verbose:
+        print(f"auc_samples: {auc_samples}")
+    landmarks = v_to_l is not None and len(v_to_l) > 0  # divergence.jl:44
+    if verbose:
+        print(f"Graph has {no_vertices} vertices and {no_edges} edges")
+        if landmarks:
+            ie = _i64(init_edges)
+            print(f"Original graph has {int(ie.max())} vertices and {ie.shape[0]} edges")
+    comm = np.asarray(comm)
+    if comm.reshape(-1).shape[0] != no_vertices:        # divergence.jl:50 (before anything else)
+        raise AssertionError(_ASSERTS[_lib.ERR_ASSERT_COMM])
+    if verbose:
+        print(f"Graph has {int(comm.max())} communities")
+        print(f"Embedding has {np.asarray(embed).shape[1]} dimensions")
+    if len(distances) != no_vertices:                   # divergence.jl:81
+        raise AssertionError(_ASSERTS[_lib.ERR_ASSERT_DIST])
+    if samples is None and auc_samples > 0:
+        adj_edges = init_edges if landmarks else edges  # divergence.jl:95-102
+        adj_w = init_eweights if landmarks else eweights
+        adj_n = len(init_vweights) if landmarks else no_vertices
+        samples = draw_samples(adj_edges, adj_w, adj_n, int(auc_samples), int(seed), directed,
+                               exact=not landmarks)
+    problem, keep = make_problem(edges, eweights, comm, embed, distances, vweights,
+                                 init_vweights if landmarks else None,
+                                 v_to_l if landmarks else None,
+                                 init_embed if landmarks else None, split, directed, samples,
+                                 max_alphas, driver)
+    own = scorer is None
+    sc = Scorer() if own else scorer
+    try:
+        sc.upload(problem, keep)
+        out, stats = sc.run()
+    finally:
+        if own:
+            sc.close()
+    sys.stderr.write("." * int(stats.n_alpha_run) + "\n")  # divergence.jl:140,255
+    if verbose and directed and out.shape[0] == 6:
+        print("Graph is a star in respect to either in or out edges")
+    return (out, stats) if return_stats else out
+
+
+def wGCL(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l, init_edges,
+         init_eweights, init_embed, split, seed=-1, auc_samples=10000, verbose=False, *,
+         samples=None, return_stats=False, max_alphas=0, driver=0, scorer=None):
+    """Weighted Geometric Chung-Lu fit + global/local divergence (divergence.jl:27-257).
+
+    Positional arguments and the returned ``[best_alpha, best_div, best_div_ext, best_div_int,
+    best_alpha_auc, best_auc, best_auc_err]`` are the reference's.  Keyword-only extras:
+    ``samples`` (pre-drawn pairs, see :func:`draw_samples`), ``return_stats``, ``max_alphas``,
+    ``driver`` and ``scorer`` (a reusable :class:`Scorer`).
+    """
+    return _score(False, edges, eweights, comm, embed, distances, vweights, init_vweights,
+                  v_to_l, init_edges, init_eweights, init_embed, split, seed, auc_samples,
+                  verbose, samples, return_stats, max_alphas, driver, scorer)
+
+
+def wGCL_directed(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
+                  init_edges, init_eweights, init_embed, split, seed=-1, auc_samples=10000,
+                  verbose=False, *, samples=None, return_stats=False, max_alphas=0, driver=0,
+                  scorer=None):
+    """Directed variant (divergence.jl:282-561); 6-element ``[-1,0,0,0,0,0]`` for a star graph."""
+    return _score(True, edges, eweights, comm, embed, distances, vweights, init_vweights,
+                  v_to_l, init_edges, init_eweights, init_embed, split, seed, auc_samples,
+                  verbose, samples, return_stats, max_alphas, driver, scorer)

@@ -1,0 +1,162 @@
+/*
+ * cge_b200.h -- C ABI of libcge_b200.so: the B200-native scoring path of CGE.jl.
+ *
+ * The reference has no FFI for this path; the seam is the Julia call
+ *     wGCL(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
+ *          init_edges, init_eweights, init_embed, split, seed, auc_samples, verbose)
+ * (/root/reference/src/divergence.jl:27-31) and wGCL_directed (divergence.jl:282-286), made from
+ * example/CGE_CLI.jl:18-24.  Each entry point below is what a `ccall` from a Julia wrapper of
+ * those two functions binds (see INTEGRATION.md and julia/CGEB200.jl); plain pointers and
+ * sizes only, the caller owns every buffer, the library only reads inputs during the call.
+ *
+ * There is no CPU fallback: without a usable CUDA device every compute entry point fails
+ * with CGE_B200_ERR_CUDA.
+ */
+#ifndef CGE_B200_H
+#define CGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGE_B200_VERSION_MAJOR 0
+#define CGE_B200_VERSION_MINOR 1
+#define CGE_B200_VERSION_PATCH 0
+
+/* alpha grid 0.25:0.25:10.0 (divergence.jl:36-37,139) */
+#define CGE_B200_N_ALPHA 40
+
+/* status codes (0 = success).  The Julia/Python wrappers turn ERR_ASSERT_* into the same
+ * AssertionError messages the reference raises (divergence.jl:50,81,303,363). */
+enum {
+    CGE_B200_OK = 0,
+    CGE_B200_ERR_ARG = -1,            /* NULL pointer / bad size / bad struct_size */
+    CGE_B200_ERR_ASSERT_COMM = -2,    /* "No. communities not matching no. vertices" */
+    CGE_B200_ERR_ASSERT_DIST = -3,    /* "Distances vector length is not equal to no. vertices" */
+    CGE_B200_ERR_OOM = -4,            /* device or host allocation failed */
+    CGE_B200_ERR_CUDA = -5,           /* no device, launch or runtime failure */
+    CGE_B200_ERR_NCCL = -6,
+    CGE_B200_ERR_STATE = -7           /* run() before upload(), comm not initialised, ... */
+};
+
+/* how the alpha loop is driven on the device */
+enum {
+    CGE_B200_DRIVER_AUTO = 0,
+    CGE_B200_DRIVER_HOSTLOOP = 1,     /* one launch per pass, host reads the residual */
+    CGE_B200_DRIVER_PERSISTENT = 2    /* one cooperative launch runs the whole alpha grid */
+};
+
+/*
+ * One scoring problem = the argument list of wGCL / wGCL_directed.
+ * Index arrays hold `index_base`-based ids (1 when passed straight from Julia).
+ * Matrices are addressed as base[row*row_stride + col*col_stride] (in elements), so Julia's
+ * column-major Matrix{Float64} (row_stride 1, col_stride = size(A,1)) and C row-major
+ * arrays are both accepted without a copy.
+ */
+typedef struct cge_b200_problem {
+    int32_t struct_size;          /* sizeof(cge_b200_problem), ABI check */
+    int32_t index_base;           /* 0 or 1 */
+    int32_t directed;             /* 0: wGCL, 1: wGCL_directed */
+    int32_t split;                /* --split-global (divergence.jl:235-241) */
+
+    /* scored graph (the landmark graph in landmark mode) */
+    int64_t m;                    /* size(edges,1) */
+    const int64_t *edge_src;      /* edges[:,1] */
+    const int64_t *edge_dst;      /* edges[:,2] */
+    const double *eweights;       /* m */
+    int64_t n_comm;               /* size(comm,1) */
+    const int64_t *comm;          /* comm[:,1], index_base-based community ids */
+    const double *embed;          /* size(embed) = embed_rows x d */
+    int64_t embed_rows, d, embed_row_stride, embed_col_stride;
+    int64_t n_distances;          /* length(distances) */
+    const double *distances;      /* diagonal of the distance matrix */
+    const double *vweights;       /* vertex (landmark) weights, >= n entries */
+
+    /* landmark mode iff n_full > 0 (= length(v_to_l), divergence.jl:44) */
+    int64_t n_full;
+    const double *init_vweights;  /* n_full */
+    const int64_t *v_to_l;        /* n_full, index_base-based landmark id per vertex */
+    const double *init_embed;     /* n_full x d */
+    int64_t init_row_stride, init_col_stride;
+
+    /* sampled pairs for the local score, drawn by the host wrapper exactly where the reference
+     * draws them (divergence.jl:184-210, 484-513).  n_sets = 1 when seeded (the same sets for
+     * every alpha), CGE_B200_N_ALPHA when seed = -1.  Arrays are n_sets x n_samples, set-major;
+     * ids refer to the ORIGINAL graph.  n_samples = 0 skips the local score. */
+    int64_t n_samples, n_sets;
+    const int64_t *pos_i, *pos_j; /* sampled edges */
+    const double *pos_w;          /* their weights (auc_weights) */
+    const int64_t *neg_i, *neg_j; /* sampled non-edges */
+
+    /* tuning; 0 = default */
+    int32_t max_alphas;           /* evaluate only the first max_alphas grid points (<= 40) */
+    int32_t driver;               /* CGE_B200_DRIVER_* */
+} cge_b200_problem;
+
+/* filled by run()/score(); everything a roofline computation or a parity test needs */
+typedef struct cge_b200_stats {
+    int32_t struct_size;
+    int32_t n_alpha_run;                    /* alphas for which the fixed point ran */
+    int32_t iters[CGE_B200_N_ALPHA];        /* fixed-point passes per alpha */
+    double div[CGE_B200_N_ALPHA];           /* global score per alpha (NaN when skipped) */
+    double auc[CGE_B200_N_ALPHA];           /* local score per alpha (NaN when skipped) */
+    double lo, hi;                          /* extrema of the raw distances (divergence.jl:92) */
+    double hi_full;                         /* landmark mode: max full-graph distance (:113) */
+    int64_t n, n_pairs;                     /* scored vertices; n(n+1)/2 */
+    int64_t fp_sweeps, b_sweeps;            /* passes over the pair matrix: fixed point / B */
+    int64_t matrix_bytes;                   /* bytes of the stored q matrix */
+    int64_t launches;                       /* kernels launched by this library in the call */
+    int32_t n_tiles, grid, driver, n_ranks;
+    float ms_upload;                        /* H2D + host preprocessing */
+    float ms_build;                         /* distance tiles + normalisation (CUDA events) */
+    float ms_solve;                         /* the alpha loop (CUDA events) */
+    float ms_total;                         /* wall clock of the call */
+    float ms_sweeps;                        /* sum of the fixed-point sweep kernels (CUDA events) */
+    float ms_bsweeps;                       /* sum of the B sweep kernels (CUDA events) */
+} cge_b200_stats;
+
+typedef struct cge_b200_handle cge_b200_handle;
+
+/* library / device discovery */
+void cge_b200_version(int *major, int *minor, int *patch);
+int cge_b200_device_count(void);             /* 0 when no CUDA device is usable */
+const char *cge_b200_last_error(void);       /* thread-local message of the last failure */
+
+/* One-shot drop-in for a single wGCL / wGCL_directed call on device 0.
+ * out has room for 7 doubles; *out_len is 7, or 6 for the directed star-graph early exit
+ * (divergence.jl:332-334).  stats may be NULL. */
+int cge_b200_score(const cge_b200_problem *p, double *out, int32_t *out_len,
+                   cge_b200_stats *stats);
+
+/* Handle API: keeps device buffers between calls and separates the host->device stage from
+ * the device-resident run (bench.py times them separately). */
+int cge_b200_create(int device, cge_b200_handle **out);
+void cge_b200_destroy(cge_b200_handle *h);
+int cge_b200_upload(cge_b200_handle *h, const cge_b200_problem *p);
+int cge_b200_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_stats *stats);
+
+/* Multi-GPU exact mode, one rank per process: every rank uploads the same problem, owns a
+ * contiguous range of pair-matrix tiles and all-reduces the n-length partial degree sums
+ * once per pass (NCCL).  id_bytes = cge_b200_comm_id_size() bytes obtained on rank 0 from
+ * cge_b200_comm_unique_id() and broadcast by the caller (e.g. torch.distributed). */
+int cge_b200_comm_id_size(void);
+int cge_b200_comm_unique_id(void *id_bytes);
+int cge_b200_comm_init(cge_b200_handle *h, const void *id_bytes, int rank, int n_ranks);
+
+/* Host-only: the tile range [*tile_begin, *tile_end) of the upper-triangular tile sequence
+ * that `rank` of `n_ranks` owns for an n-vertex problem, and the tile count. No GPU needed. */
+int cge_b200_shard_plan(int64_t n, int rank, int n_ranks, int64_t *n_tiles,
+                        int64_t *tile_begin, int64_t *tile_end);
+
+/* Debug / parity probes (used by tests): copy device state of the last upload()/run() back.
+ * what: 0 = dense n x n row-major matrix of q = (1 - D)^(1/4) in the caller's vertex order,
+ *       1 = T (or Tin) in the caller's order, 2 = Tout, 3 = last S (or Sin), 4 = last Sout.
+ * n_elems is the capacity of buf in doubles. */
+int cge_b200_debug_read(cge_b200_handle *h, int what, double *buf, int64_t n_elems);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGE_B200_H */

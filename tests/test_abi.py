@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads, exports every symbol include/cge_b200.h declares, its structs
+match the ctypes mirror, and it fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from cge_jl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cge_b200.h")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cge_b200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _lib.load()
+    syms = declared_symbols()
+    assert len(syms) >= 13
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in cge_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_struct_layout_matches_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include "cge_b200.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+                   "int main(){printf(\"%zu %zu %zu %zu %zu\\n\", sizeof(cge_b200_problem),"
+                   "sizeof(cge_b200_stats), offsetof(cge_b200_problem, n_samples),"
+                   "offsetof(cge_b200_stats, lo), offsetof(cge_b200_stats, ms_sweeps));return 0;}\n")
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.dirname(HEADER), str(src), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    assert got == [C.sizeof(_lib.Problem), C.sizeof(_lib.Stats), _lib.Problem.n_samples.offset,
+                   _lib.Stats.lo.offset, _lib.Stats.ms_sweeps.offset]
+
+
+def test_version():
+    a, b, c = C.c_int(), C.c_int(), C.c_int()
+    _lib.load().cge_b200_version(C.byref(a), C.byref(b), C.byref(c))
+    assert (a.value, b.value, c.value) == (0, 1, 0)
+
+
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    if lib.cge_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    rc = lib.cge_b200_create(0, C.byref(h))
+    assert rc == _lib.ERR_CUDA and not h.value
+    assert "no CPU fallback" in _lib.last_error()
+    from cge_jl_b200 import divergence as dv
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dv.Scorer(0)
+    # the one-shot entry point fails the same way
+    p = _lib.Problem()
+    out = np.zeros(7)
+    n_out = C.c_int32()
+    rc = lib.cge_b200_score(C.byref(p), out.ctypes.data_as(C.POINTER(C.c_double)),
+                            C.byref(n_out), None)
+    assert rc == _lib.ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "cge_jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
+                assert "libcge_oracle" not in txt, f
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 10000, 200000])
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_shard_plan_partitions_the_tile_sequence(n, world):
+    nb = (n + 127) // 128
+    prev_end = 0
+    for r in range(world):
+        nt, b, e = _lib.shard_plan(n, r, world)
+        assert nt == nb * (nb + 1) // 2
+        assert b == prev_end and e >= b
+        prev_end = e
+        assert abs((e - b) - nt / world) <= 1
+    assert prev_end == nt
