@@ -205,9 +205,12 @@ def run_b200(args):
     out = last["out"]
     a_run = int(stats.n_alpha_run)
     # end to end through the public call: host buffers, H2D + D2H inside the timed region
-    for _ in range(max(1, args.warmup // 3)):
-        step_e2e()
-    dt_e2e = timed(step_e2e, args.steps)
+    if args.no_e2e:
+        dt_e2e = float("nan")
+    else:
+        for _ in range(max(1, args.warmup // 3)):
+            step_e2e()
+        dt_e2e = timed(step_e2e, args.steps)
     sampler.stop_flag = True
     if rank != 0:
         if world > 1:
@@ -271,6 +274,7 @@ def main():
     ap.add_argument("--ref-alphas", type=int, default=2,
                     help="alpha values per CPU sample (bounds the CPU baseline's run time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -1,0 +1,66 @@
+"""Turns the files a profiling gpurun call leaves in gpurun_out/ into the committed summaries.
+
+  python profiles/summarize.py launches gpurun_out/launches_r01.csv > profiles/r01_launches.txt
+  python profiles/summarize.py raw gpurun_out/prof_sweep_r01.ncu-rep > profiles/r01_sweep_full.txt
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct", "l1tex__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "launch__grid_size", "launch__block_size", "launch__waves_per_multiprocessor",
+    "smsp__inst_executed.sum", "sm__cycles_elapsed.max", "smsp__cycles_active.avg",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__sass_inst_executed_op_global_ld.sum", "sm__sass_inst_executed_op_shared_ld.sum",
+]
+
+
+def launches(path):
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for row in csv.DictReader(lines):
+        name = re.sub(r"[<(].*", "", row["Kernel Name"]).replace("void ", "")
+        v = float(row["Metric Value"].replace(",", ""))
+        v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(row["Metric Unit"], 1.0)
+        agg[name][0] += 1
+        agg[name][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path})")
+    print(f"# {sum(v[0] for v in agg.values())} launches, {tot:.1f} us of kernel time "
+          "(cold-cache, serialised: compare shares, not absolutes)")
+    print(f"{'kernel':28s} {'launches':>8s} {'total_us':>12s} {'avg_us':>9s} {'share':>6s}")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:28s} {v[0]:8d} {v[1]:12.1f} {v[1] / v[0]:9.2f} {v[1] / tot:6.3f}")
+
+
+def raw(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                         text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    print(f"# ncu --set full --clock-control none --import-source on  ({path})")
+    for r in data:
+        print(f"\n== {r[hdr.index('Kernel Name')]}  grid {r[hdr.index('Grid Size')]} "
+              f"block {r[hdr.index('Block Size')]}")
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                print(f"{k:80s} {r[i]:>16s} {units[i]}")
+
+
+if __name__ == "__main__":
+    {"launches": launches, "raw": raw}[sys.argv[1]](sys.argv[2])
