@@ -48,6 +48,15 @@ void launch_tiles(int m, int kind, int grid, cudaStream_t stream, const SweepArg
     }
 }
 
+const void *fp_kernel(int m, int directed) {
+    switch ((m - 1) / 10) {
+        case 0: return fp_kernel_part0(m, directed);
+        case 1: return fp_kernel_part1(m, directed);
+        case 2: return fp_kernel_part2(m, directed);
+        default: return fp_kernel_part3(m, directed);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------
@@ -206,14 +215,24 @@ __device__ __forceinline__ void block_max_to_slot(double e, unsigned long long *
     }
 }
 
-// sum of the per-block partials in fixed order
-__global__ void k_reduce_part(const double *__restrict__ part, int nb, int np, int n,
-                              double *__restrict__ sraw) {
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n) return;
-    double s = 0.0;
-    for (int b = 0; b < nb; ++b) s += __ldcg(part + (size_t)b * np + v);
-    sraw[v] = s;
+// sum of the per-block partial slots in fixed order: a CTA takes 32 vertices, warp w adds the
+// slots b = w, w+8, ... (coalesced 256-byte rows), warp 0 adds the eight sub-sums
+__global__ void __launch_bounds__(NTHREADS)
+k_reduce_part(const double *__restrict__ part, int nb, int np, int n, double *__restrict__ sraw) {
+    __shared__ double s_red[NWARPS * 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int v = blockIdx.x * 32 + lane;
+    double p = 0.0;
+    if (v < n)
+        for (int b = w; b < nb; b += NWARPS) p += __ldcg(part + (size_t)b * np + v);
+    s_red[w * 32 + lane] = p;
+    __syncthreads();
+    if (w == 0 && v < n) {
+        double s = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < NWARPS; ++w2) s += s_red[w2 * 32 + lane];
+        sraw[v] = s;
+    }
 }
 
 // divergence.jl:160-166: S_i = T_i * sum, T_i += eps*T_i*(w_i/S_i - 1), diff = max|w_i - S_i|
@@ -438,7 +457,7 @@ struct cge_b200_handle {
     std::vector<uint8_t> bin_internal;   // vect_I (divergence.jl:66-71 / 348-351)
     // device
     DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
-        sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out;
+        sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out, fpres;
     DevBuf s_pda, s_pdb, s_nda, s_ndb, s_pa, s_pb, s_na, s_nb, s_pw, s_pw0a, s_pwla, s_pw0b, s_pwlb, s_nw0a, s_nwla, s_nw0b,
         s_nwlb, s_pq, s_nq;
     float ms_upload = 0.f;
@@ -487,7 +506,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     h->landmark = p->n_full > 0;
     h->max_alphas = p->max_alphas > 0 ? std::min<int>(p->max_alphas, CGE_B200_N_ALPHA)
                                       : CGE_B200_N_ALPHA;
-    h->driver = p->driver == CGE_B200_DRIVER_AUTO ? CGE_B200_DRIVER_HOSTLOOP : p->driver;
+    h->driver = p->driver;
     // no_vertices = maximum(edges) (divergence.jl:41 / :294)
     int64_t n = 0;
     for (int64_t e = 0; e < p->m; ++e) {
@@ -639,6 +658,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     if ((rc = h->lohi.ensure(64))) return rc;
     if ((rc = h->slots.ensure(64))) return rc;
     if ((rc = h->auc_out.ensure(64))) return rc;
+    if ((rc = h->fpres.ensure(64))) return rc;
 
     // landmark mode: original graph arrays for the local score
     if (h->landmark && h->K > 0) {
@@ -746,7 +766,11 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     S.n = h->n;
     S.n_pairs = h->n * (h->n + 1) / 2;
     S.n_ranks = h->n_ranks;
-    S.driver = h->driver;
+    // the persistent kernel cannot call NCCL between passes: multi-rank runs use the host loop
+    const int driver = h->n_ranks > 1 ? CGE_B200_DRIVER_HOSTLOOP
+                       : h->driver == CGE_B200_DRIVER_AUTO ? CGE_B200_DRIVER_PERSISTENT
+                                                           : h->driver;
+    S.driver = driver;
     S.ms_upload = h->ms_upload;
     if (h->star) {  // divergence.jl:332-334
         out[0] = -1.0;
@@ -848,6 +872,18 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     A.partB = h->partB.as<double>();
     A.comm = h->comm.as<int>();
     A.B = h->B.as<double>();
+    A.Tw_a = h->Ta.as<double>();
+    A.Tw_b = h->Tb.as<double>();
+    A.w_a = h->w.as<double>();
+    A.w_b = h->w2.as<double>();
+    A.qdiag = h->qdiag.as<double>();
+    A.S_a = h->Sa.as<double>();
+    A.S_b = h->Sb.as<double>();
+    A.slots = h->slots.as<unsigned long long>();
+    A.delta = 0.001;
+    A.max_iter = 200000;
+    A.out_iters = reinterpret_cast<int *>(h->fpres.as<char>());
+    A.out_diff = reinterpret_cast<double *>(h->fpres.as<char>() + 8);
 
     SampleSide sp, sn;
     if (h->K > 0) {
@@ -879,7 +915,33 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         const double alpha = 0.25 * m;
         double diff = 1.0, eps = h->directed ? 0.9 : 0.25;  // :150,:34 / :434-435
         int it = 0;
-        while (diff > delta) {  // :151 / :436
+        if (driver == CGE_B200_DRIVER_PERSISTENT) {
+            // one cooperative launch runs every pass of this alpha
+            const void *fn = fp_kernel(m, h->directed);
+            int bps = 0;
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, NTHREADS, 0));
+            if (bps < 1) return fail(CGE_B200_ERR_CUDA, "fixed-point kernel does not fit on an SM");
+            const int want = std::max(local_tiles, (n + 31) / 32);
+            const int cgrid = std::max(1, std::min(want, bps * h->sm_count));
+            A.eps0 = eps;
+            CUDA_TRY(cudaMemsetAsync(h->slots.p, 0, 64, st));
+            void *kargs[] = {(void *)&A};
+            cudaEventRecord(h->next_event(), st);
+            CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(cgrid), dim3(NTHREADS), kargs, 0, st));
+            cudaEventRecord(h->next_event(), st);
+            h->ev_is_b.push_back(0);
+            ++h->launches;
+            S.grid = cgrid;
+            struct { int it; int pad; double diff; } res;
+            CUDA_TRY(cudaMemcpyAsync(&res, h->fpres.p, 16, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            it = res.it;
+            diff = res.diff;
+            S.fp_sweeps += it;
+            if (it >= A.max_iter)
+                return fail(CGE_B200_ERR_STATE, "fixed point did not converge in 200000 passes");
+        }
+        while (driver != CGE_B200_DRIVER_PERSISTENT && diff > delta) {  // :151 / :436
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
                 launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
@@ -887,10 +949,12 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 h->ev_is_b.push_back(0);
                 ++h->launches;
             }
-            k_reduce_part<<<ublocks, 256, 0, st>>>(A.partA, nb, np, n, h->sraw_a.as<double>());
+            k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A.partA, nb, np, n,
+                                                              h->sraw_a.as<double>());
             ++h->launches;
             if (h->directed) {
-                k_reduce_part<<<ublocks, 256, 0, st>>>(A.partB, nb, np, n, h->sraw_b.as<double>());
+                k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A.partB, nb, np, n,
+                                                                  h->sraw_b.as<double>());
                 ++h->launches;
             }
             if (h->n_ranks > 1) {
@@ -1074,7 +1138,7 @@ void cge_b200_destroy(cge_b200_handle *h) {
     for (DevBuf *b :
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
-          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
+          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
           &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})
         b->release();

@@ -38,4 +38,25 @@ void CGE_CAT(launch_tiles_part, CGE_PART)(int m, int kind, int grid, cudaStream_
     }
 }
 
+#define CGE_FP_CASE(MM)                                                       \
+    case MM:                                                                  \
+        return directed ? (const void *)k_fixed_point<MM, true>               \
+                        : (const void *)k_fixed_point<MM, false>;
+
+const void *CGE_CAT(fp_kernel_part, CGE_PART)(int m, int directed) {
+    switch (m) {
+        CGE_FP_CASE(CGE_PART * 10 + 1)
+        CGE_FP_CASE(CGE_PART * 10 + 2)
+        CGE_FP_CASE(CGE_PART * 10 + 3)
+        CGE_FP_CASE(CGE_PART * 10 + 4)
+        CGE_FP_CASE(CGE_PART * 10 + 5)
+        CGE_FP_CASE(CGE_PART * 10 + 6)
+        CGE_FP_CASE(CGE_PART * 10 + 7)
+        CGE_FP_CASE(CGE_PART * 10 + 8)
+        CGE_FP_CASE(CGE_PART * 10 + 9)
+        CGE_FP_CASE(CGE_PART * 10 + 10)
+        default: return nullptr;
+    }
+}
+
 }  // namespace cge

@@ -13,6 +13,7 @@
 // Each slot part[b][v] is written by exactly one tile, so the reduction over b done by the
 // finalize kernel has a fixed order (bit-reproducible, no atomics).
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -36,6 +37,17 @@ struct SweepArgs {
     double *partB;         //                                   directed: Sout partials
     const int *comm;       // [np] community per (sorted) vertex, -1 on pads
     double *B;             // [k][k] expected community mass (divergence.jl:228-234 / 532-538)
+    // persistent fixed-point kernel only
+    double *Tw_a, *Tw_b;   // the same T arrays, writable
+    const double *w_a;     // target degrees: undirected vweights, directed degree_in
+    const double *w_b;     //                                     directed degree_out
+    const double *qdiag;   // q_ii (directed: the diagonal term is counted twice)
+    double *S_a, *S_b;     // last S (Sin / Sout), for probes
+    unsigned long long *slots;  // [3] residual slots, zero on entry
+    double eps0, delta;
+    int max_iter;
+    int *out_iters;        // passes executed
+    double *out_diff;      // last residual
 };
 
 // q^M with a fixed multiplication chain (binary powering), M = 4*alpha in 1..40
@@ -362,9 +374,107 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_bsweep(const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Persistent fixed point of one alpha (divergence.jl:150-168 / 434-467) as ONE cooperative
+// launch: every pass is [tiles] -> grid.sync -> [reduce partials, update T, residual] ->
+// grid.sync, so the host is out of the loop (no launch or D2H per pass).  All control flow is
+// computed identically by every thread from the residual slot.
+// ---------------------------------------------------------------------------------------------
+template <int M, bool DIRECTED>
+__global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_constant__ SweepArgs a) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ __align__(16) double s_col[2][(DIRECTED ? 2 : 1) * NWARPS * TILE];
+    __shared__ double s_red[(DIRECTED ? 2 : 1) * NWARPS * 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ngroups = (a.n + 31) / 32;
+    double diff = 1.0, eps = a.eps0;
+    int it = 0, tile_it = 0;
+    while (diff > a.delta && it < a.max_iter) {
+        for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++tile_it) {
+            const int2 ij = a.tile_ij[t];
+            const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
+            if (DIRECTED)
+                tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1]);
+            else
+                tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1]);
+        }
+        grid.sync();
+        // 32 vertices per CTA step: warp w sums the partial slots b = w, w+8, ..., warp 0 adds
+        // the eight sub-sums in fixed order and applies divergence.jl:160-165 / 451-461
+        double e = 0.0;
+        for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+            const int v = g * 32 + lane;
+            double pa = 0.0, pb = 0.0;
+            if (v < a.n) {
+                for (int b = w; b < a.nb; b += NWARPS) {
+                    pa += __ldcg(a.partA + (size_t)b * a.np + v);
+                    if (DIRECTED) pb += __ldcg(a.partB + (size_t)b * a.np + v);
+                }
+            }
+            s_red[w * 32 + lane] = pa;
+            if (DIRECTED) s_red[NWARPS * 32 + w * 32 + lane] = pb;
+            __syncthreads();
+            if (w == 0 && v < a.n) {
+                double sa = 0.0, sb = 0.0;
+#pragma unroll
+                for (int w2 = 0; w2 < NWARPS; ++w2) {
+                    sa += s_red[w2 * 32 + lane];
+                    if (DIRECTED) sb += s_red[NWARPS * 32 + w2 * 32 + lane];
+                }
+                if (!DIRECTED) {
+                    const double t = __ldcg(a.Ta + v), wv = a.w_a[v];
+                    const double s = t * sa;
+                    a.Tw_a[v] = t + eps * t * (wv / s - 1.0);
+                    a.S_a[v] = s;
+                    e = fmax(e, fabs(wv - s));
+                } else {
+                    const double ti = __ldcg(a.Ta + v), to = __ldcg(a.Tb + v);
+                    const double gd = powm<M>(a.qdiag[v]);
+                    const double sin = ti * (sa + to * gd), sout = to * (sb + ti * gd);
+                    a.S_a[v] = sin;
+                    a.S_b[v] = sout;
+                    const double di = a.w_a[v], dout = a.w_b[v];
+                    if (di > 0.0) {
+                        a.Tw_a[v] = ti + eps * ti * (di / sin - 1.0);
+                        e = fmax(e, fabs(di - sin));
+                    }
+                    if (dout > 0.0) {
+                        a.Tw_b[v] = to + eps * to * (dout / sout - 1.0);
+                        e = fmax(e, fabs(dout - sout));
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (w == 0) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) e = fmax(e, __shfl_xor_sync(FULL, e, off));
+            if (lane == 0)
+                atomicMax(a.slots + it % 3, (unsigned long long)__double_as_longlong(e));
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.slots[(it + 1) % 3] = 0ull;
+        grid.sync();
+        const double f = __longlong_as_double((long long)__ldcg(a.slots + it % 3));
+        if (DIRECTED && f > diff) eps *= 0.99;  // divergence.jl:462-464
+        diff = f;
+        ++it;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *a.out_iters = it;
+        *a.out_diff = diff;
+    }
+}
+
 // host-side dispatch over the compile-time exponent; defined in cge_inst_*.cu
 // kind: 0 = sweep undirected, 1 = sweep directed, 2 = B undirected, 3 = B directed
+// fp_kernel(m, directed) returns the cooperative fixed-point kernel for cudaLaunchCooperativeKernel
 void launch_tiles(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+const void *fp_kernel(int m, int directed);
+const void *fp_kernel_part0(int m, int directed);
+const void *fp_kernel_part1(int m, int directed);
+const void *fp_kernel_part2(int m, int directed);
+const void *fp_kernel_part3(int m, int directed);
 void launch_tiles_part0(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part1(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part2(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);

@@ -16,7 +16,7 @@ README_GOLDEN = [6.25, 0.002961243353776198]  # /root/reference/README.md:99, el
 
 
 def run_pair(scorer, directed, edges, ew, comm, emb, dist, vw, lm_args=None, split=False,
-             seed=42, K=2000, samples="draw"):
+             seed=42, K=2000, samples="draw", driver=0):
     """Score on the GPU and with the oracle using the same sampled pairs."""
     if lm_args is None:
         init_vw, v2l, init_edges, init_ew, init_emb = EMPTY
@@ -29,7 +29,8 @@ def run_pair(scorer, directed, edges, ew, comm, emb, dist, vw, lm_args=None, spl
     f_gpu = dv.wGCL_directed if directed else dv.wGCL
     out, stats = f_gpu(edges, ew, comm, emb, dist, vw, init_vw, v2l, init_edges, init_ew,
                        init_emb, split, seed, K, False, samples=samples, return_stats=True,
-                       scorer=scorer)
+                       scorer=scorer, driver=driver)
+    assert stats.driver == (driver or 2)
     f_ref = oracle.wgcl_directed if directed else oracle.wgcl
     ref, tr = f_ref(edges, ew, comm, emb, dist, vw, init_vw if lm_args else None,
                     v2l if lm_args else None, init_emb if lm_args else None, split, samples)
@@ -65,9 +66,14 @@ def test_one_pass_degrees(scorer):
     assert np.all(T > 0)
 
 
-def test_exact_undirected_test_graph(scorer):
+DRIVERS = pytest.mark.parametrize("driver", [1, 2], ids=["hostloop", "persistent"])
+
+
+@DRIVERS
+def test_exact_undirected_test_graph(scorer, driver):
     edges, ew, vw, comm, emb = load_fixture("test115.npz")
-    out, stats, ref, tr = run_pair(scorer, False, edges, ew, comm, emb, np.zeros(115), vw)
+    out, stats, ref, tr = run_pair(scorer, False, edges, ew, comm, emb, np.zeros(115), vw,
+                                   driver=driver)
     assert_parity(out, stats, ref, tr)
     assert out[0] == 3.25 and np.isclose(out[1], 0.006929334486296551, rtol=RTOL)
 
@@ -81,9 +87,11 @@ def test_exact_undirected_split_global(scorer):
     assert np.isclose(out[1], (out[2] + out[3]) / 2, rtol=1e-12)
 
 
-def test_exact_directed_weighted_test_graph(scorer):
+@DRIVERS
+def test_exact_directed_weighted_test_graph(scorer, driver):
     edges, ew, vw, comm, emb = load_fixture("test115_weighted.npz")
-    out, stats, ref, tr = run_pair(scorer, True, edges, ew, comm, emb, np.zeros(115), vw)
+    out, stats, ref, tr = run_pair(scorer, True, edges, ew, comm, emb, np.zeros(115), vw,
+                                   driver=driver)
     assert_parity(out, stats, ref, tr)
     assert out[0] == 5.5 and np.isclose(out[1], 0.008821457041054588, rtol=RTOL)
 
@@ -118,13 +126,15 @@ def test_landmark_mode_test_graph(scorer, directed):
     assert np.isclose(stats.hi_full, tr.hi_full, rtol=1e-15)
 
 
+@DRIVERS
 @pytest.mark.parametrize("directed,n,k,d", [(False, 700, 5, 20), (True, 520, 7, 33),
                                             (False, 129, 3, 16), (False, 256, 40, 8)])
-def test_synthetic_multi_tile(scorer, directed, n, k, d):
+def test_synthetic_multi_tile(scorer, directed, n, k, d, driver):
     """Several 128-tiles, ragged last tile, d not a multiple of 16, many small communities."""
     edges, ew, vw, comm, emb = planted_partition(n, k, d, seed=n + k, directed=directed,
                                                  weighted=True)
-    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw, K=3000)
+    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw, K=3000,
+                                   driver=driver)
     assert_parity(out, stats, ref, tr)
 
 
@@ -166,7 +176,8 @@ def test_readme_golden_landmarks_10k(scorer):
     assert 0.0 <= out[5] < 0.01 and out[4] >= 7.5
 
 
-def test_exact_10k_against_frozen_oracle(scorer):
+@DRIVERS
+def test_exact_10k_against_frozen_oracle(scorer, driver):
     """BASELINE.json configs[1]: 10k example --force-exact, vs tests/golden/oracle_example10k_exact.npz."""
     import os
     from util import GOLDEN
@@ -175,7 +186,7 @@ def test_exact_10k_against_frozen_oracle(scorer):
     samples = tuple(g[k].astype(np.int64) if k != "pos_w" else g[k]
                     for k in ("pos_i", "pos_j", "pos_w", "neg_i", "neg_j"))
     out, stats = dv.wGCL(edges, ew, comm, emb, np.zeros(10000), vw, *EMPTY, False, 42, 10000,
-                         False, samples=samples, return_stats=True, scorer=scorer)
+                         False, samples=samples, return_stats=True, scorer=scorer, driver=driver)
 
     class Tr:
         n_alpha_run = int(g["n_alpha_run"])

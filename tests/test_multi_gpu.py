@@ -1,0 +1,90 @@
+"""GPU (>= 2 devices): the tile-sharded exact mode.  Two ranks (one process per GPU) own halves
+of the tile sequence and all-reduce the partial degree sums every pass over NCCL; the result
+must match the single-GPU run (identical pass counts and best alphas, scores within 1e-9) and
+the CPU oracle.  Skipped on a one-GPU box; run with `gpurun --gpus 2`."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _problem(directed):
+    from util import planted_partition
+    n = 1500
+    edges, ew, vw, comm, emb = planted_partition(n, 9, 24, seed=77, directed=directed, weighted=True)
+    return n, edges, ew, vw, comm, emb
+
+
+def _worker(rank, world, port, directed, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    from cge_jl_b200 import divergence as dv
+    n, edges, ew, vw, comm, emb = _problem(directed)
+    samples = dv.draw_samples(edges, ew, n, 2000, 42, directed, True)
+    sc = dv.Scorer(rank)
+    ids = [dv.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    sc.comm_init(ids[0], rank, world)
+    p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False,
+                              directed, samples)
+    sc.upload(p, keep)
+    out, st = sc.run()
+    dist.barrier()
+    if rank == 0:
+        q.put((out, list(st.iters), list(st.div), list(st.auc), int(st.n_ranks), int(st.driver)))
+    sc.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_two_gpu_matches_one_gpu_and_oracle(directed):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    import oracle
+    from cge_jl_b200 import divergence as dv
+    from util import RTOL, assert_parity, empty_landmark_args
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, directed, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out2, iters2, div2, auc2, n_ranks, driver = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert n_ranks == 2 and driver == 1
+    n, edges, ew, vw, comm, emb = _problem(directed)
+    samples = dv.draw_samples(edges, ew, n, 2000, 42, directed, True)
+    f = dv.wGCL_directed if directed else dv.wGCL
+    out1, st1 = f(edges, ew, comm, emb, np.zeros(n), vw, *empty_landmark_args(), False, 42, 2000,
+                  False, samples=samples, return_stats=True)
+    assert list(st1.iters) == iters2
+    assert out1[0] == out2[0] and out1[4] == out2[4]
+    np.testing.assert_allclose(out2, out1, rtol=RTOL, atol=1e-15)
+    fo = oracle.wgcl_directed if directed else oracle.wgcl
+    ref, tr = fo(edges, ew, comm, emb, np.zeros(n), vw, samples=samples)
+
+    class St:
+        n_alpha_run = tr.n_alpha_run
+        iters, div, auc = iters2, div2, auc2
+    assert_parity(out2, St, ref, tr)
