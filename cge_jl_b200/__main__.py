@@ -1,0 +1,30 @@
+"""``python -m cge_jl_b200 -g G -e E [-c C] [flags]`` -- the CGE_CLI.jl driver
+(/root/reference/example/CGE_CLI.jl:1-25) on top of the B200 scorer; same flags, same output."""
+import numpy as np
+
+from . import landmarks, parseargs
+from .divergence import wGCL, wGCL_directed
+
+
+def main(argv=None):
+    (edges, weights, vweights, comm, clusters, embed, verbose, land, forced, method, directed,
+     split, seed, samples) = parseargs(argv)
+    distances = np.zeros(vweights.shape[0])
+    init_edges = np.zeros((0, 0), dtype=np.int64)
+    init_vweights, init_eweights = np.zeros(0), np.zeros(0)
+    init_embed = np.zeros((0, 0))
+    v_to_l = np.zeros(0, dtype=np.int64)
+    if land != -1:
+        init_edges, init_vweights = edges.copy(), vweights.copy()
+        init_eweights, init_embed = weights.copy(), embed.copy()
+        distances, embed, comm, edges, weights, vweights, v_to_l = landmarks(
+            edges, weights, vweights, clusters, comm, embed, verbose, land, forced, method, directed)
+    f = wGCL_directed if directed else wGCL
+    results = f(edges, weights, comm, embed, distances, vweights, init_vweights, v_to_l,
+                init_edges, init_eweights, init_embed, split, seed, samples, verbose)
+    print([float(x) for x in results])
+    return results
+
+
+if __name__ == "__main__":
+    main()
