@@ -882,6 +882,12 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     A.slots = h->slots.as<unsigned long long>();
     A.delta = 0.001;
     A.max_iter = 200000;
+    {
+        // L2-resident share of the matrix (MB); CGE_B200_L2_MB overrides the default
+        double mb = 64.0;
+        if (const char *e = getenv("CGE_B200_L2_MB")) mb = atof(e);
+        A.resident_tiles = (long long)(mb * 1e6 / (TILE_ELEMS * 8.0));
+    }
     A.out_iters = reinterpret_cast<int *>(h->fpres.as<char>());
     A.out_diff = reinterpret_cast<double *>(h->fpres.as<char>() + 8);
 

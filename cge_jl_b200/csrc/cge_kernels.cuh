@@ -48,6 +48,7 @@ struct SweepArgs {
     int max_iter;
     int *out_iters;        // passes executed
     double *out_diff;      // last residual
+    long long resident_tiles;  // local tiles [0, resident_tiles) are kept in L2 (evict_last)
 };
 
 // q^M with a fixed multiplication chain (binary powering), M = 4*alpha in 1..40
@@ -73,12 +74,21 @@ __device__ __forceinline__ double powm_rt(double q, int m) {
     return r;
 }
 
-// streaming 16-byte load of matrix data: read once per pass, keep it out of L1
-__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+// 16-byte load of matrix data: read once per pass, kept out of L1.  The L2 policy decides what
+// survives from one pass to the next: the first `resident_tiles` tiles are loaded evict_last (they
+// stay in the 126 MB L2 across passes), the rest evict_first (they stream through without
+// displacing the resident set) -- a cyclic sweep under plain LRU would hit nothing.
+__device__ __forceinline__ uint64_t l2_policy(bool keep) {
+    uint64_t pl, pf;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+    return keep ? pl : pf;
+}
+__device__ __forceinline__ double2 ld_stream(const double2 *p, uint64_t pol) {
     double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
                  : "=d"(v.x), "=d"(v.y)
-                 : "l"(p));
+                 : "l"(p), "l"(pol));
     return v;
 }
 
@@ -128,7 +138,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ---------------------------------------------------------------------------------------------
 template <int M>
 __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int bi, int bj,
-                                            const SweepArgs &a, double *s_col) {
+                                            const SweepArgs &a, double *s_col, uint64_t pol) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = w * ROWS_PER_WARP;
     const double *Tc = a.Ta + (size_t)bj * TILE;
@@ -141,8 +151,8 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
-        const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane);
-        const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane);
+        const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
+        const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
         const double ti = __shfl_sync(FULL, trow, rr);
         const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
         const double g2 = powm<M>(v23.x), g3 = powm<M>(v23.y);
@@ -180,7 +190,7 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
 // ---------------------------------------------------------------------------------------------
 template <int M>
 __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int bi, int bj,
-                                            const SweepArgs &a, double *s_col) {
+                                            const SweepArgs &a, double *s_col, uint64_t pol) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = w * ROWS_PER_WARP;
     const double *Tic = a.Ta + (size_t)bj * TILE, *Toc = a.Tb + (size_t)bj * TILE;
@@ -200,8 +210,8 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
 #pragma unroll
         for (int r8 = 0; r8 < 8; ++r8) {
             const int rr = batch * 8 + r8;
-            const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane);
-            const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane);
+            const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
+            const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
             const double t_in = __shfl_sync(FULL, trow_in, rr);
             const double t_out = __shfl_sync(FULL, trow_out, rr);
             const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
@@ -270,7 +280,7 @@ __device__ __forceinline__ void flush_bins(double v, int bin_col, long long bin_
 
 template <int M, bool DIRECTED>
 __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi, int bj,
-                                           const SweepArgs &a) {
+                                           const SweepArgs &a, uint64_t pol) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = w * ROWS_PER_WARP;
     const int gc0 = bj * TILE + 2 * lane, gc2 = bj * TILE + 64 + 2 * lane;
@@ -318,8 +328,8 @@ __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi
         double2 v01[4], v23[4];
 #pragma unroll
         for (int r8 = 0; r8 < 4; ++r8) {
-            v01[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + lane);
-            v23[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + 32 + lane);
+            v01[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + lane, pol);
+            v23[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + 32 + lane, pol);
         }
 #pragma unroll
         for (int r8 = 0; r8 < 4; ++r8) {
@@ -359,10 +369,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_sweep(const __grid_constant__ S
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++it) {
         const int2 ij = a.tile_ij[t];
         const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
+        const uint64_t pol = l2_policy(t - a.tile_begin < a.resident_tiles);
         if (DIRECTED)
-            tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[it & 1]);
+            tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[it & 1], pol);
         else
-            tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[it & 1]);
+            tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[it & 1], pol);
     }
 }
 
@@ -370,7 +381,8 @@ template <int M, bool DIRECTED>
 __global__ void __launch_bounds__(NTHREADS, 2) k_bsweep(const __grid_constant__ SweepArgs a) {
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x) {
         const int2 ij = a.tile_ij[t];
-        tile_bpass<M, DIRECTED>(a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS, ij.x, ij.y, a);
+        tile_bpass<M, DIRECTED>(a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS, ij.x, ij.y, a,
+                                l2_policy(t - a.tile_begin < a.resident_tiles));
     }
 }
 
@@ -394,10 +406,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
         for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++tile_it) {
             const int2 ij = a.tile_ij[t];
             const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
+            const uint64_t pol = l2_policy(t - a.tile_begin < a.resident_tiles);
             if (DIRECTED)
-                tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1]);
+                tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1], pol);
             else
-                tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1]);
+                tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1], pol);
         }
         grid.sync();
         // 32 vertices per CTA step: warp w sums the partial slots b = w, w+8, ..., warp 0 adds
