@@ -240,7 +240,11 @@ def run_b200(args):
                          % (stats.matrix_bytes / 1e6),
                    "driver": {1: "hostloop", 2: "persistent"}.get(int(stats.driver), "?"),
                    "result": [float(x) for x in out],
-                   "device_ms_per_step": float(np.mean(ev_ms))},
+                   "device_ms_per_step": float(np.mean(ev_ms)),
+                   "ms_breakdown_last_step": {
+                       "upload": float(stats.ms_upload), "build": float(stats.ms_build),
+                       "solve": float(stats.ms_solve), "fp_kernels": float(stats.ms_sweeps),
+                       "b_kernels": float(stats.ms_bsweeps), "total": float(stats.ms_total)}},
         "clocks": sampler.summary(),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt_e2e / args.steps},

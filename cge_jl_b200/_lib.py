@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcge_b200.so")
 
 OK, ERR_ARG, ERR_ASSERT_COMM, ERR_ASSERT_DIST, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_STATE = (
     0, -1, -2, -3, -4, -5, -6, -7)
-DRIVER_AUTO, DRIVER_HOSTLOOP, DRIVER_PERSISTENT = 0, 1, 2
+DRIVER_AUTO, DRIVER_HOSTLOOP, DRIVER_PERSISTENT, DRIVER_RING = 0, 1, 2, 3
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int64)

@@ -8,6 +8,7 @@
 // section 8(a).
 #include "../../include/cge_b200.h"
 #include "cge_kernels.cuh"
+#include "cge_ring.cuh"
 
 #include <dlfcn.h>
 
@@ -56,6 +57,19 @@ const void *fp_kernel(int m, int directed) {
         default: return fp_kernel_part3(m, directed);
     }
 }
+
+const void *fp_ring_kernel(int m, int directed) {
+    switch ((m - 1) / 10) {
+        case 0: return fp_ring_kernel_part0(m, directed);
+        case 1: return fp_ring_kernel_part1(m, directed);
+        case 2: return fp_ring_kernel_part2(m, directed);
+        default: return fp_ring_kernel_part3(m, directed);
+    }
+}
+size_t fp_ring_smem_bytes(int directed) {
+    return directed ? ring_smem_bytes<true>() : ring_smem_bytes<false>();
+}
+int fp_ring_threads() { return RING_THREADS; }
 
 // ---------------------------------------------------------------------------------------------
 // small kernels
@@ -303,12 +317,16 @@ __device__ __forceinline__ double sample_value(const SampleSide &s, long long i,
     return fa * fb * powm_rt(s.q[i], m);
 }
 
-__global__ void __launch_bounds__(1024)
+constexpr int AUC_THREADS = 256, AUC_MAX_BLOCKS = 64;
+// block b handles samples [b*chunk, (b+1)*chunk) and writes its (sum of winning weights, sum of
+// weights) to out[2b], out[2b+1]; the host adds the per-block pairs in block order.
+__global__ void __launch_bounds__(AUC_THREADS)
 k_auc(SampleSide pos, SampleSide neg, const double *__restrict__ wts, long long offset,
-      int K, const double *Ta, const double *Tb, int m, double *out2) {
-    __shared__ double s_num[1024], s_den[1024];
+      int K, int chunk, const double *Ta, const double *Tb, int m, double *out) {
+    __shared__ double s_num[AUC_THREADS], s_den[AUC_THREADS];
     double num = 0.0, den = 0.0;
-    for (int s = threadIdx.x; s < K; s += blockDim.x) {
+    const int s0 = blockIdx.x * chunk, s1 = min(K, s0 + chunk);
+    for (int s = s0 + threadIdx.x; s < s1; s += AUC_THREADS) {
         const long long i = offset + s;
         const double pv = sample_value(pos, i, Ta, Tb, m);
         const double nv = sample_value(neg, i, Ta, Tb, m);
@@ -319,7 +337,7 @@ k_auc(SampleSide pos, SampleSide neg, const double *__restrict__ wts, long long 
     s_num[threadIdx.x] = num;
     s_den[threadIdx.x] = den;
     __syncthreads();
-    for (int h = blockDim.x >> 1; h > 0; h >>= 1) {
+    for (int h = AUC_THREADS >> 1; h > 0; h >>= 1) {
         if ((int)threadIdx.x < h) {
             s_num[threadIdx.x] += s_num[threadIdx.x + h];
             s_den[threadIdx.x] += s_den[threadIdx.x + h];
@@ -327,8 +345,8 @@ k_auc(SampleSide pos, SampleSide neg, const double *__restrict__ wts, long long 
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        out2[0] = s_num[0];
-        out2[1] = s_den[0];
+        out[2 * blockIdx.x] = s_num[0];
+        out[2 * blockIdx.x + 1] = s_den[0];
     }
 }
 
@@ -462,6 +480,20 @@ struct cge_b200_handle {
         s_nwlb, s_pq, s_nq;
     float ms_upload = 0.f;
     int64_t launches = 0;
+    void *pinned = nullptr;           // page-locked staging for the per-alpha results
+    size_t pinned_cap = 0;
+    int ensure_pinned(size_t bytes) {
+        if (bytes <= pinned_cap) return 0;
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr;
+        pinned_cap = 0;
+        if (cudaMallocHost(&pinned, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(CGE_B200_ERR_OOM, "cudaMallocHost failed");
+        }
+        pinned_cap = bytes;
+        return 0;
+    }
     std::vector<cudaEvent_t> evpool;  // pairs of events around every sweep launch
     size_t ev_used = 0;
     std::vector<uint8_t> ev_is_b;
@@ -657,7 +689,8 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     if ((rc = h->B.ensure(std::max<size_t>((size_t)(k * k) * 8, 16)))) return rc;
     if ((rc = h->lohi.ensure(64))) return rc;
     if ((rc = h->slots.ensure(64))) return rc;
-    if ((rc = h->auc_out.ensure(64))) return rc;
+    if ((rc = h->auc_out.ensure(2 * AUC_MAX_BLOCKS * 8))) return rc;
+    if ((rc = h->ensure_pinned(64 + 2 * AUC_MAX_BLOCKS * 8 + (size_t)(k * k) * 8))) return rc;
     if ((rc = h->fpres.ensure(64))) return rc;
 
     // landmark mode: original graph arrays for the local score
@@ -767,9 +800,11 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     S.n_pairs = h->n * (h->n + 1) / 2;
     S.n_ranks = h->n_ranks;
     // the persistent kernel cannot call NCCL between passes: multi-rank runs use the host loop
-    const int driver = h->n_ranks > 1 ? CGE_B200_DRIVER_HOSTLOOP
-                       : h->driver == CGE_B200_DRIVER_AUTO ? CGE_B200_DRIVER_PERSISTENT
-                                                           : h->driver;
+    const int driver =
+        h->n_ranks > 1 ? CGE_B200_DRIVER_HOSTLOOP
+        : h->driver == CGE_B200_DRIVER_AUTO
+            ? CGE_B200_DRIVER_PERSISTENT  // measured: 65.3 us/pass vs 72.2 for the TMA ring (r01)
+            : h->driver;
     S.driver = driver;
     S.ms_upload = h->ms_upload;
     if (h->star) {  // divergence.jl:332-334
@@ -884,7 +919,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     A.max_iter = 200000;
     {
         // L2-resident share of the matrix (MB); CGE_B200_L2_MB overrides the default
-        double mb = 64.0;
+        double mb = 80.0;
         if (const char *e = getenv("CGE_B200_L2_MB")) mb = atof(e);
         A.resident_tiles = (long long)(mb * 1e6 / (TILE_ELEMS * 8.0));
     }
@@ -921,11 +956,17 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         const double alpha = 0.25 * m;
         double diff = 1.0, eps = h->directed ? 0.9 : 0.25;  // :150,:34 / :434-435
         int it = 0;
-        if (driver == CGE_B200_DRIVER_PERSISTENT) {
+        if (driver == CGE_B200_DRIVER_PERSISTENT || driver == CGE_B200_DRIVER_RING) {
             // one cooperative launch runs every pass of this alpha
-            const void *fn = fp_kernel(m, h->directed);
+            const bool ring = driver == CGE_B200_DRIVER_RING;
+            const void *fn = ring ? fp_ring_kernel(m, h->directed) : fp_kernel(m, h->directed);
+            const int threads = ring ? fp_ring_threads() : NTHREADS;
+            const size_t smem = ring ? fp_ring_smem_bytes(h->directed) : 0;
+            if (ring)
+                CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
             int bps = 0;
-            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, NTHREADS, 0));
+            CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, threads, smem));
             if (bps < 1) return fail(CGE_B200_ERR_CUDA, "fixed-point kernel does not fit on an SM");
             const int want = std::max(local_tiles, (n + 31) / 32);
             const int cgrid = std::max(1, std::min(want, bps * h->sm_count));
@@ -933,21 +974,15 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             CUDA_TRY(cudaMemsetAsync(h->slots.p, 0, 64, st));
             void *kargs[] = {(void *)&A};
             cudaEventRecord(h->next_event(), st);
-            CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(cgrid), dim3(NTHREADS), kargs, 0, st));
+            CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(cgrid), dim3(threads), kargs, smem, st));
             cudaEventRecord(h->next_event(), st);
             h->ev_is_b.push_back(0);
             ++h->launches;
             S.grid = cgrid;
-            struct { int it; int pad; double diff; } res;
-            CUDA_TRY(cudaMemcpyAsync(&res, h->fpres.p, 16, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            it = res.it;
-            diff = res.diff;
-            S.fp_sweeps += it;
-            if (it >= A.max_iter)
-                return fail(CGE_B200_ERR_STATE, "fixed point did not converge in 200000 passes");
+            // its result (pass count, residual) is fetched together with the scores below
+            CUDA_TRY(cudaMemcpyAsync(h->pinned, h->fpres.p, 16, cudaMemcpyDeviceToHost, st));
         }
-        while (driver != CGE_B200_DRIVER_PERSISTENT && diff > delta) {  // :151 / :436
+        while (driver == CGE_B200_DRIVER_HOSTLOOP && diff > delta) {  // :151 / :436
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
                 launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
@@ -999,34 +1034,27 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             if (it >= 200000)
                 return fail(CGE_B200_ERR_STATE, "fixed point did not converge in 200000 passes");
         }
-        S.iters[m - 1] = it;
-        S.n_alpha_run = m;
-        // ---- local score (divergence.jl:178-224 / 478-528) ----
-        if (!skip_auc) {
+        // ---- local score (divergence.jl:178-224 / 478-528) and global score (:226-252 /
+        // :530-556): both kernels are queued behind the fixed point, one sync per alpha ----
+        char *pin = static_cast<char *>(h->pinned);
+        double *pin_auc = reinterpret_cast<double *>(pin + 64);
+        double *pin_B = reinterpret_cast<double *>(pin + 64 + 2 * AUC_MAX_BLOCKS * 8);
+        const bool do_auc = !skip_auc, do_div = !skip_div;
+        int auc_blocks = 0;
+        if (do_auc) {
             const long long off = (h->n_sets > 1 ? (long long)(m - 1) : 0) * h->K;
             // undirected: T_a*T_b; directed: Tout of the source, Tin of the target (:488-490,:507)
             const double *fa = h->directed ? h->Tb.as<double>() : h->Ta.as<double>();
             const double *fb = h->Ta.as<double>();
-            k_auc<<<1, 1024, 0, st>>>(sp, sn, h->s_pw.as<double>(), off, (int)h->K, fa, fb, m,
-                                      h->auc_out.as<double>());
+            auc_blocks = (int)std::min<int64_t>(AUC_MAX_BLOCKS, (h->K + AUC_THREADS - 1) / AUC_THREADS);
+            const int chunk = (int)((h->K + auc_blocks - 1) / auc_blocks);
+            k_auc<<<auc_blocks, AUC_THREADS, 0, st>>>(sp, sn, h->s_pw.as<double>(), off, (int)h->K,
+                                                      chunk, fa, fb, m, h->auc_out.as<double>());
             ++h->launches;
-            double r2[2];
-            CUDA_TRY(cudaMemcpyAsync(r2, h->auc_out.p, 16, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            const double auc = 1.0 - r2[0] / r2[1];  // :213
-            S.auc[m - 1] = auc;
-            if (auc < best_auc) {  // :215-223
-                best_auc = auc;
-                best_auc_err = 1.96 * std::sqrt(auc * (1.0 - auc) / (double)h->K);
-                best_alpha_auc = alpha;
-                alpha_auc_counter = 5;
-            } else {
-                alpha_auc_counter -= 1;
-                skip_auc = alpha_auc_counter == 0;
-            }
+            CUDA_TRY(cudaMemcpyAsync(pin_auc, h->auc_out.p, (size_t)auc_blocks * 16,
+                                     cudaMemcpyDeviceToHost, st));
         }
-        // ---- global score (divergence.jl:226-252 / 530-556) ----
-        if (!skip_div) {
+        if (do_div) {
             CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
@@ -1041,9 +1069,38 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                                                          kNcclSum, h->nccl_comm, st),
                                         "ncclAllReduce(B)"))
                     return rc;
-            CUDA_TRY(cudaMemcpyAsync(Bh.data(), h->B.p, (size_t)k * k * 8, cudaMemcpyDeviceToHost,
-                                     st));
-            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMemcpyAsync(pin_B, h->B.p, (size_t)k * k * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (driver != CGE_B200_DRIVER_HOSTLOOP) {
+            std::memcpy(&it, pin, 4);
+            std::memcpy(&diff, pin + 8, 8);
+            S.fp_sweeps += it;
+            if (it >= A.max_iter)
+                return fail(CGE_B200_ERR_STATE, "fixed point did not converge in 200000 passes");
+        }
+        S.iters[m - 1] = it;
+        S.n_alpha_run = m;
+        if (do_auc) {
+            double num = 0.0, den = 0.0;
+            for (int b = 0; b < auc_blocks; ++b) {
+                num += pin_auc[2 * b];
+                den += pin_auc[2 * b + 1];
+            }
+            const double auc = 1.0 - num / den;  // :213
+            S.auc[m - 1] = auc;
+            if (auc < best_auc) {  // :215-223
+                best_auc = auc;
+                best_auc_err = 1.96 * std::sqrt(auc * (1.0 - auc) / (double)h->K);
+                best_alpha_auc = alpha;
+                alpha_auc_counter = 5;
+            } else {
+                alpha_auc_counter -= 1;
+                skip_auc = alpha_auc_counter == 0;
+            }
+        }
+        if (do_div) {
+            std::memcpy(Bh.data(), pin_B, (size_t)k * k * 8);
             double f, div_int = 0.0, div_ext = 0.0;
             if (!h->split) {
                 f = js_bins(h->C, Bh, h->bins, h->bin_internal, 0, 1);
@@ -1149,6 +1206,7 @@ void cge_b200_destroy(cge_b200_handle *h) {
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})
         b->release();
     for (cudaEvent_t e : h->evpool) cudaEventDestroy(e);
+    if (h->pinned) cudaFreeHost(h->pinned);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }

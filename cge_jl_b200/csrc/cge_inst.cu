@@ -1,6 +1,7 @@
 // cge_inst.cu -- instantiates the tile kernels for ten exponents per translation unit
 // (compiled four times with -DCGE_PART=0..3 so the 160 instantiations build in parallel).
 #include "cge_kernels.cuh"
+#include "cge_ring.cuh"
 
 #ifndef CGE_PART
 #error "compile with -DCGE_PART=0..3"
@@ -55,6 +56,27 @@ const void *CGE_CAT(fp_kernel_part, CGE_PART)(int m, int directed) {
         CGE_FP_CASE(CGE_PART * 10 + 8)
         CGE_FP_CASE(CGE_PART * 10 + 9)
         CGE_FP_CASE(CGE_PART * 10 + 10)
+        default: return nullptr;
+    }
+}
+
+#define CGE_RING_CASE(MM)                                                     \
+    case MM:                                                                  \
+        return directed ? (const void *)k_fixed_point_ring<MM, true>          \
+                        : (const void *)k_fixed_point_ring<MM, false>;
+
+const void *CGE_CAT(fp_ring_kernel_part, CGE_PART)(int m, int directed) {
+    switch (m) {
+        CGE_RING_CASE(CGE_PART * 10 + 1)
+        CGE_RING_CASE(CGE_PART * 10 + 2)
+        CGE_RING_CASE(CGE_PART * 10 + 3)
+        CGE_RING_CASE(CGE_PART * 10 + 4)
+        CGE_RING_CASE(CGE_PART * 10 + 5)
+        CGE_RING_CASE(CGE_PART * 10 + 6)
+        CGE_RING_CASE(CGE_PART * 10 + 7)
+        CGE_RING_CASE(CGE_PART * 10 + 8)
+        CGE_RING_CASE(CGE_PART * 10 + 9)
+        CGE_RING_CASE(CGE_PART * 10 + 10)
         default: return nullptr;
     }
 }

@@ -266,15 +266,23 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void flush_bins(double v, int bin_col, long long bin_base,
                                            long long col_stride, double *B, int lane) {
-    // v: this lane's contribution for community bin_col (or -1 on pads)
-    const int b0 = __shfl_sync(FULL, bin_col, 0);
-    if (__all_sync(FULL, bin_col == b0)) {
-        if (b0 >= 0) {
-            const double s = warp_sum(v);
-            if (lane == 0) atomicAdd(B + bin_base + (long long)b0 * col_stride, s);
+    // v: this lane's contribution for community bin_col (or -1 on pads).  Columns are sorted by
+    // community, so a warp sees one or two communities: one masked warp reduction and one FP64
+    // atomic per community present; beyond four communities the rest goes lane by lane.
+    unsigned rem = __ballot_sync(FULL, bin_col >= 0);
+    int round = 0;
+    while (rem) {  // warp-uniform
+        if (round++ == 4) {
+            if (((rem >> lane) & 1u) && v != 0.0)
+                atomicAdd(B + bin_base + (long long)bin_col * col_stride, v);
+            break;
         }
-    } else if (bin_col >= 0 && v != 0.0) {
-        atomicAdd(B + bin_base + (long long)bin_col * col_stride, v);
+        const int leader = __ffs(rem) - 1;
+        const int key = __shfl_sync(FULL, bin_col, leader);
+        const bool in = bin_col == key;
+        const double s = warp_sum(in ? v : 0.0);
+        if (lane == leader) atomicAdd(B + bin_base + (long long)key * col_stride, s);
+        rem &= ~__ballot_sync(FULL, in);
     }
 }
 
@@ -323,24 +331,42 @@ __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi
         for (int k = 0; k < 4; ++k) accA[k] = accB[k] = 0.0;
     };
 
+    // rows are taken in batches of four with the loads of the next batch issued before the
+    // current one is consumed (register double buffering); a batch whose rows all share the
+    // current row community (the common case after the community sort) runs without any per-row
+    // check
+    constexpr int BR = 4, NB = ROWS_PER_WARP / BR;
+    double2 v01[2][BR], v23[2][BR];
 #pragma unroll
-    for (int batch = 0; batch < 4; ++batch) {
-        double2 v01[4], v23[4];
+    for (int r8 = 0; r8 < BR; ++r8) {
+        v01[0][r8] = ld_stream(base + r8 * (TILE / 2) + lane, pol);
+        v23[0][r8] = ld_stream(base + r8 * (TILE / 2) + 32 + lane, pol);
+    }
 #pragma unroll
-        for (int r8 = 0; r8 < 4; ++r8) {
-            v01[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + lane, pol);
-            v23[r8] = ld_stream(base + (batch * 4 + r8) * (TILE / 2) + 32 + lane, pol);
-        }
+    for (int batch = 0; batch < NB; ++batch) {
+        const int cb = batch & 1, nb_ = cb ^ 1;
+        if (batch + 1 < NB) {
 #pragma unroll
-        for (int r8 = 0; r8 < 4; ++r8) {
-            const int rr = batch * 4 + r8;
-            const int cr = __shfl_sync(FULL, crow, rr);
-            if (cr != cur) {  // warp-uniform
-                flush(cur);
-                cur = cr;
+            for (int r8 = 0; r8 < BR; ++r8) {
+                v01[nb_][r8] = ld_stream(base + ((batch + 1) * BR + r8) * (TILE / 2) + lane, pol);
+                v23[nb_][r8] =
+                    ld_stream(base + ((batch + 1) * BR + r8) * (TILE / 2) + 32 + lane, pol);
             }
-            double g[4] = {powm<M>(v01[r8].x), powm<M>(v01[r8].y), powm<M>(v23[r8].x),
-                           powm<M>(v23[r8].y)};
+        }
+        const unsigned bm = ((1u << BR) - 1u) << (batch * BR);
+        const bool uniform = (__ballot_sync(FULL, crow != cur) & bm) == 0u;
+#pragma unroll
+        for (int r8 = 0; r8 < BR; ++r8) {
+            const int rr = batch * BR + r8;
+            if (!uniform) {
+                const int cr = __shfl_sync(FULL, crow, rr);
+                if (cr != cur) {  // warp-uniform
+                    flush(cur);
+                    cur = cr;
+                }
+            }
+            double g[4] = {powm<M>(v01[cb][r8].x), powm<M>(v01[cb][r8].y),
+                           powm<M>(v23[cb][r8].x), powm<M>(v23[cb][r8].y)};
             if (!DIRECTED && diag) {  // unordered pairs once: keep col >= row (divergence.jl:229-230)
                 const int gr = bi * TILE + row0 + rr;
 #pragma unroll
@@ -488,6 +514,14 @@ const void *fp_kernel_part0(int m, int directed);
 const void *fp_kernel_part1(int m, int directed);
 const void *fp_kernel_part2(int m, int directed);
 const void *fp_kernel_part3(int m, int directed);
+// the same fixed point with the matrix streamed by cp.async.bulk through a shared-memory ring
+const void *fp_ring_kernel(int m, int directed);
+const void *fp_ring_kernel_part0(int m, int directed);
+const void *fp_ring_kernel_part1(int m, int directed);
+const void *fp_ring_kernel_part2(int m, int directed);
+const void *fp_ring_kernel_part3(int m, int directed);
+size_t fp_ring_smem_bytes(int directed);
+int fp_ring_threads();
 void launch_tiles_part0(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part1(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part2(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);

@@ -45,7 +45,8 @@ enum {
 enum {
     CGE_B200_DRIVER_AUTO = 0,
     CGE_B200_DRIVER_HOSTLOOP = 1,     /* one launch per pass, host reads the residual */
-    CGE_B200_DRIVER_PERSISTENT = 2    /* one cooperative launch runs the whole alpha grid */
+    CGE_B200_DRIVER_PERSISTENT = 2,   /* one cooperative launch per alpha runs all its passes */
+    CGE_B200_DRIVER_RING = 3          /* same, matrix streamed by cp.async.bulk through a smem ring */
 };
 
 /*

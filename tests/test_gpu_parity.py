@@ -30,7 +30,7 @@ def run_pair(scorer, directed, edges, ew, comm, emb, dist, vw, lm_args=None, spl
     out, stats = f_gpu(edges, ew, comm, emb, dist, vw, init_vw, v2l, init_edges, init_ew,
                        init_emb, split, seed, K, False, samples=samples, return_stats=True,
                        scorer=scorer, driver=driver)
-    assert stats.driver == (driver or 2)
+    assert driver == 0 or stats.driver == driver
     f_ref = oracle.wgcl_directed if directed else oracle.wgcl
     ref, tr = f_ref(edges, ew, comm, emb, dist, vw, init_vw if lm_args else None,
                     v2l if lm_args else None, init_emb if lm_args else None, split, samples)
@@ -66,7 +66,7 @@ def test_one_pass_degrees(scorer):
     assert np.all(T > 0)
 
 
-DRIVERS = pytest.mark.parametrize("driver", [1, 2], ids=["hostloop", "persistent"])
+DRIVERS = pytest.mark.parametrize("driver", [1, 2, 3], ids=["hostloop", "persistent", "ring"])
 
 
 @DRIVERS
