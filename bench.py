@@ -157,7 +157,8 @@ def run_b200(args):
         dist.broadcast_object_list(ids, src=0)
         sc.comm_init(ids[0], rank, world)
     problem, keep = dv.make_problem(w["edges"], w["ew"], w["comm"], w["emb"], np.zeros(n), w["vw"],
-                                    None, None, None, False, False, w["samples"], 0, args.driver)
+                                    None, None, None, False, False, w["samples"], 0, args.driver,
+                                    args.regime)
     h2d = sum(a.nbytes for a in keep)
     d2h = 7 * 8
 
@@ -238,7 +239,8 @@ def run_b200(args):
                    "pairs": pairs, "samples_local": 10000, "tiles": int(stats.n_tiles),
                    "l2": "inputs larger than L2 (q matrix %.0f MB per GPU vs 126 MB L2)"
                          % (stats.matrix_bytes / 1e6),
-                   "driver": {1: "hostloop", 2: "persistent"}.get(int(stats.driver), "?"),
+                   "driver": {1: "hostloop", 2: "persistent", 3: "ring"}.get(int(stats.driver), "?"),
+                   "regime": {1: "stored", 2: "recompute"}.get(int(stats.regime), "?"),
                    "result": [float(x) for x in out],
                    "device_ms_per_step": float(np.mean(ev_ms)),
                    "ms_breakdown_last_step": {
@@ -275,6 +277,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--driver", type=int, default=0, help="0 auto, 1 host loop, 2 persistent")
+    ap.add_argument("--regime", type=int, default=0, help="0 auto, 1 stored, 2 recompute")
     ap.add_argument("--ref-alphas", type=int, default=2,
                     help="alpha values per CPU sample (bounds the CPU baseline's run time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

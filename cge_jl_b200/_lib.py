@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcge_b200.so")
 OK, ERR_ARG, ERR_ASSERT_COMM, ERR_ASSERT_DIST, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_STATE = (
     0, -1, -2, -3, -4, -5, -6, -7)
 DRIVER_AUTO, DRIVER_HOSTLOOP, DRIVER_PERSISTENT, DRIVER_RING = 0, 1, 2, 3
+REGIME_AUTO, REGIME_STORED, REGIME_RECOMPUTE = 0, 1, 2
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int64)
@@ -33,6 +34,7 @@ class Problem(C.Structure):
         ("n_samples", C.c_int64), ("n_sets", C.c_int64),
         ("pos_i", _pi), ("pos_j", _pi), ("pos_w", _pd), ("neg_i", _pi), ("neg_j", _pi),
         ("max_alphas", C.c_int32), ("driver", C.c_int32),
+        ("regime", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -46,7 +48,7 @@ class Stats(C.Structure):
         ("fp_sweeps", C.c_int64), ("b_sweeps", C.c_int64),
         ("matrix_bytes", C.c_int64), ("launches", C.c_int64),
         ("n_tiles", C.c_int32), ("grid", C.c_int32), ("driver", C.c_int32),
-        ("n_ranks", C.c_int32),
+        ("n_ranks", C.c_int32), ("regime", C.c_int32), ("reserved", C.c_int32),
         ("ms_upload", C.c_float), ("ms_build", C.c_float), ("ms_solve", C.c_float),
         ("ms_total", C.c_float), ("ms_sweeps", C.c_float), ("ms_bsweeps", C.c_float),
     ]

@@ -41,29 +41,41 @@ static int fail(int code, const std::string &msg) {
     } while (0)
 
 void launch_tiles(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a) {
-    switch ((m - 1) / 10) {
+    switch ((m - 1) / 5) {
         case 0: launch_tiles_part0(m, kind, grid, stream, a); break;
         case 1: launch_tiles_part1(m, kind, grid, stream, a); break;
         case 2: launch_tiles_part2(m, kind, grid, stream, a); break;
-        default: launch_tiles_part3(m, kind, grid, stream, a); break;
+        case 3: launch_tiles_part3(m, kind, grid, stream, a); break;
+        case 4: launch_tiles_part4(m, kind, grid, stream, a); break;
+        case 5: launch_tiles_part5(m, kind, grid, stream, a); break;
+        case 6: launch_tiles_part6(m, kind, grid, stream, a); break;
+        default: launch_tiles_part7(m, kind, grid, stream, a); break;
     }
 }
 
 const void *fp_kernel(int m, int directed) {
-    switch ((m - 1) / 10) {
+    switch ((m - 1) / 5) {
         case 0: return fp_kernel_part0(m, directed);
         case 1: return fp_kernel_part1(m, directed);
         case 2: return fp_kernel_part2(m, directed);
-        default: return fp_kernel_part3(m, directed);
+        case 3: return fp_kernel_part3(m, directed);
+        case 4: return fp_kernel_part4(m, directed);
+        case 5: return fp_kernel_part5(m, directed);
+        case 6: return fp_kernel_part6(m, directed);
+        default: return fp_kernel_part7(m, directed);
     }
 }
 
 const void *fp_ring_kernel(int m, int directed) {
-    switch ((m - 1) / 10) {
+    switch ((m - 1) / 5) {
         case 0: return fp_ring_kernel_part0(m, directed);
         case 1: return fp_ring_kernel_part1(m, directed);
         case 2: return fp_ring_kernel_part2(m, directed);
-        default: return fp_ring_kernel_part3(m, directed);
+        case 3: return fp_ring_kernel_part3(m, directed);
+        case 4: return fp_ring_kernel_part4(m, directed);
+        case 5: return fp_ring_kernel_part5(m, directed);
+        case 6: return fp_ring_kernel_part6(m, directed);
+        default: return fp_ring_kernel_part7(m, directed);
     }
 }
 size_t fp_ring_smem_bytes(int directed) {
@@ -464,6 +476,7 @@ struct cge_b200_handle {
     int64_t n = 0, np = 0, nb = 0, d = 0, dp = 0, k = 0, K = 0, n_sets = 1;
     int64_t n_full = 0, npf = 0, nbf = 0;
     int max_alphas = CGE_B200_N_ALPHA, driver = CGE_B200_DRIVER_HOSTLOOP;
+    int regime = CGE_B200_REGIME_STORED;  // regime in use after upload()
     int64_t n_tiles = 0, tile_begin = 0, tile_end = 0, n_tiles_full = 0;
     // multi-rank
     int rank = 0, n_ranks = 1;
@@ -680,7 +693,22 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         CUDA_TRY(cudaStreamSynchronize(st));  // tij is a local
     }
     const size_t local_tiles = (size_t)(h->tile_end - h->tile_begin);
-    if ((rc = h->q.ensure(std::max<size_t>(local_tiles, 1) * TILE_ELEMS * 8))) return rc;
+    const size_t q_bytes = std::max<size_t>(local_tiles, 1) * TILE_ELEMS * 8;
+    h->regime = p->regime;
+    if (h->regime == CGE_B200_REGIME_AUTO) {
+        // stored when the tiles fit next to everything else (2 GB + 5 % head-room), else recompute
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t avail = free_b + h->q.cap;
+        const size_t other = (size_t)h->nb * (size_t)np * 8 * (h->directed ? 2 : 1) + ((size_t)2 << 30);
+        h->regime = q_bytes + other + total_b / 20 <= avail ? CGE_B200_REGIME_STORED
+                                                            : CGE_B200_REGIME_RECOMPUTE;
+    }
+    if (h->regime == CGE_B200_REGIME_STORED) {
+        if ((rc = h->q.ensure(q_bytes))) return rc;
+    } else {
+        h->q.release();
+    }
     const size_t part_bytes = (size_t)h->nb * (size_t)np * 8;
     if ((rc = h->partA.ensure(part_bytes))) return rc;
     if (h->directed && (rc = h->partB.ensure(part_bytes))) return rc;
@@ -806,6 +834,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             ? CGE_B200_DRIVER_PERSISTENT  // measured: 65.3 us/pass vs 72.2 for the TMA ring (r01)
             : h->driver;
     S.driver = driver;
+    S.regime = h->regime;
+    const bool stored = h->regime == CGE_B200_REGIME_STORED;
     S.ms_upload = h->ms_upload;
     if (h->star) {  // divergence.jl:332-334
         out[0] = -1.0;
@@ -825,7 +855,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     const int grid = std::max(1, std::min(local_tiles, 2 * h->sm_count));
     S.n_tiles = (int)h->n_tiles;
     S.grid = grid;
-    S.matrix_bytes = (int64_t)local_tiles * TILE_ELEMS * 8;
+    S.matrix_bytes = stored ? (int64_t)local_tiles * TILE_ELEMS * 8 : 0;
     cudaEvent_t ev0, ev1, ev2;
     CUDA_TRY(cudaEventCreate(&ev0));
     CUDA_TRY(cudaEventCreate(&ev1));
@@ -844,9 +874,16 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         CUDA_TRY(cudaMemcpyAsync(lohi, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
     if (local_tiles > 0) {
-        k_build_dist<true><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp, h->dist.as<double>(),
-                                                      n, h->tile_ij.as<int2>(), tb, te,
-                                                      h->q.as<double>(), lohi);
+        if (stored)
+            k_build_dist<true><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
+                                                          h->dist.as<double>(), n,
+                                                          h->tile_ij.as<int2>(), tb, te,
+                                                          h->q.as<double>(), lohi);
+        else  // recompute regime: only the extrema are needed up front
+            k_build_dist<false><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
+                                                           h->dist.as<double>(), n,
+                                                           h->tile_ij.as<int2>(), tb, te, nullptr,
+                                                           lohi);
         ++h->launches;
     }
     if (h->n_ranks > 1) {
@@ -858,7 +895,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 "ncclAllReduce(max)"))
             return rc;
     }
-    if (local_tiles > 0) {
+    if (local_tiles > 0 && stored) {
         k_transform<<<4 * h->sm_count, 256, 0, st>>>(h->q.as<double>(),
                                                      (size_t)local_tiles * TILE_ELEMS, lohi);
         ++h->launches;
@@ -925,6 +962,11 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     }
     A.out_iters = reinterpret_cast<int *>(h->fpres.as<char>());
     A.out_diff = reinterpret_cast<double *>(h->fpres.as<char>() + 8);
+    A.emb = h->emb.as<double>();
+    A.diag = h->dist.as<double>();
+    A.lohi = lohi;
+    A.dp = dp;
+    A.m = 1;
 
     SampleSide sp, sn;
     if (h->K > 0) {
@@ -954,12 +996,15 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     long long sweep_no = 0;
     for (int m = 1; m <= h->max_alphas; ++m) {
         const double alpha = 0.25 * m;
+        A.m = m;
         double diff = 1.0, eps = h->directed ? 0.9 : 0.25;  // :150,:34 / :434-435
         int it = 0;
         if (driver == CGE_B200_DRIVER_PERSISTENT || driver == CGE_B200_DRIVER_RING) {
             // one cooperative launch runs every pass of this alpha
-            const bool ring = driver == CGE_B200_DRIVER_RING;
-            const void *fn = ring ? fp_ring_kernel(m, h->directed) : fp_kernel(m, h->directed);
+            const bool ring = stored && driver == CGE_B200_DRIVER_RING;
+            const void *fn = !stored ? fp_kernel_rc(h->directed)
+                             : ring  ? fp_ring_kernel(m, h->directed)
+                                     : fp_kernel(m, h->directed);
             const int threads = ring ? fp_ring_threads() : NTHREADS;
             const size_t smem = ring ? fp_ring_smem_bytes(h->directed) : 0;
             if (ring)
@@ -985,7 +1030,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         while (driver == CGE_B200_DRIVER_HOSTLOOP && diff > delta) {  // :151 / :436
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
-                launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
+                if (stored) launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
+                else launch_tiles_rc(h->directed ? 1 : 0, grid, st, A);
                 cudaEventRecord(h->next_event(), st);
                 h->ev_is_b.push_back(0);
                 ++h->launches;
@@ -1058,7 +1104,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
-                launch_tiles(m, h->directed ? 3 : 2, grid, st, A);
+                if (stored) launch_tiles(m, h->directed ? 3 : 2, grid, st, A);
+                else launch_tiles_rc(h->directed ? 3 : 2, grid, st, A);
                 cudaEventRecord(h->next_event(), st);
                 h->ev_is_b.push_back(1);
                 ++h->launches;
@@ -1284,6 +1331,8 @@ int cge_b200_debug_read(cge_b200_handle *h, int what, double *buf, int64_t n_ele
     if (what == 0) {
         if (n_elems < n * n) return fail(CGE_B200_ERR_ARG, "buffer too small");
         if (h->n_ranks != 1) return fail(CGE_B200_ERR_STATE, "dense read needs all tiles local");
+        if (h->regime != CGE_B200_REGIME_STORED)
+            return fail(CGE_B200_ERR_STATE, "no stored matrix in the recompute regime");
         std::vector<double> tile((size_t)TILE_ELEMS);
         for (int64_t bi = 0; bi < h->nb; ++bi)
             for (int64_t bj = bi; bj < h->nb; ++bj) {

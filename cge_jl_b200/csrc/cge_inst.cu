@@ -1,10 +1,10 @@
-// cge_inst.cu -- instantiates the tile kernels for ten exponents per translation unit
-// (compiled four times with -DCGE_PART=0..3 so the 160 instantiations build in parallel).
+// cge_inst.cu -- instantiates the tile kernels for five exponents per translation unit
+// (compiled eight times with -DCGE_PART=0..7 so the instantiations build in parallel).
 #include "cge_kernels.cuh"
 #include "cge_ring.cuh"
 
 #ifndef CGE_PART
-#error "compile with -DCGE_PART=0..3"
+#error "compile with -DCGE_PART=0..7"
 #endif
 
 namespace cge {
@@ -25,16 +25,11 @@ namespace cge {
 void CGE_CAT(launch_tiles_part, CGE_PART)(int m, int kind, int grid, cudaStream_t stream,
                                           const SweepArgs &a) {
     switch (m) {
-        CGE_CASE(CGE_PART * 10 + 1)
-        CGE_CASE(CGE_PART * 10 + 2)
-        CGE_CASE(CGE_PART * 10 + 3)
-        CGE_CASE(CGE_PART * 10 + 4)
-        CGE_CASE(CGE_PART * 10 + 5)
-        CGE_CASE(CGE_PART * 10 + 6)
-        CGE_CASE(CGE_PART * 10 + 7)
-        CGE_CASE(CGE_PART * 10 + 8)
-        CGE_CASE(CGE_PART * 10 + 9)
-        CGE_CASE(CGE_PART * 10 + 10)
+        CGE_CASE(CGE_PART * 5 + 1)
+        CGE_CASE(CGE_PART * 5 + 2)
+        CGE_CASE(CGE_PART * 5 + 3)
+        CGE_CASE(CGE_PART * 5 + 4)
+        CGE_CASE(CGE_PART * 5 + 5)
         default: break;
     }
 }
@@ -46,16 +41,11 @@ void CGE_CAT(launch_tiles_part, CGE_PART)(int m, int kind, int grid, cudaStream_
 
 const void *CGE_CAT(fp_kernel_part, CGE_PART)(int m, int directed) {
     switch (m) {
-        CGE_FP_CASE(CGE_PART * 10 + 1)
-        CGE_FP_CASE(CGE_PART * 10 + 2)
-        CGE_FP_CASE(CGE_PART * 10 + 3)
-        CGE_FP_CASE(CGE_PART * 10 + 4)
-        CGE_FP_CASE(CGE_PART * 10 + 5)
-        CGE_FP_CASE(CGE_PART * 10 + 6)
-        CGE_FP_CASE(CGE_PART * 10 + 7)
-        CGE_FP_CASE(CGE_PART * 10 + 8)
-        CGE_FP_CASE(CGE_PART * 10 + 9)
-        CGE_FP_CASE(CGE_PART * 10 + 10)
+        CGE_FP_CASE(CGE_PART * 5 + 1)
+        CGE_FP_CASE(CGE_PART * 5 + 2)
+        CGE_FP_CASE(CGE_PART * 5 + 3)
+        CGE_FP_CASE(CGE_PART * 5 + 4)
+        CGE_FP_CASE(CGE_PART * 5 + 5)
         default: return nullptr;
     }
 }
@@ -67,16 +57,11 @@ const void *CGE_CAT(fp_kernel_part, CGE_PART)(int m, int directed) {
 
 const void *CGE_CAT(fp_ring_kernel_part, CGE_PART)(int m, int directed) {
     switch (m) {
-        CGE_RING_CASE(CGE_PART * 10 + 1)
-        CGE_RING_CASE(CGE_PART * 10 + 2)
-        CGE_RING_CASE(CGE_PART * 10 + 3)
-        CGE_RING_CASE(CGE_PART * 10 + 4)
-        CGE_RING_CASE(CGE_PART * 10 + 5)
-        CGE_RING_CASE(CGE_PART * 10 + 6)
-        CGE_RING_CASE(CGE_PART * 10 + 7)
-        CGE_RING_CASE(CGE_PART * 10 + 8)
-        CGE_RING_CASE(CGE_PART * 10 + 9)
-        CGE_RING_CASE(CGE_PART * 10 + 10)
+        CGE_RING_CASE(CGE_PART * 5 + 1)
+        CGE_RING_CASE(CGE_PART * 5 + 2)
+        CGE_RING_CASE(CGE_PART * 5 + 3)
+        CGE_RING_CASE(CGE_PART * 5 + 4)
+        CGE_RING_CASE(CGE_PART * 5 + 5)
         default: return nullptr;
     }
 }

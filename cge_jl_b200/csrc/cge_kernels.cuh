@@ -49,6 +49,11 @@ struct SweepArgs {
     int *out_iters;        // passes executed
     double *out_diff;      // last residual
     long long resident_tiles;  // local tiles [0, resident_tiles) are kept in L2 (evict_last)
+    // recompute regime only
+    const double *emb;     // [np][dp] sorted, zero-padded embedding
+    const double *diag;    // [np] D_ii (divergence.jl:85-86)
+    const unsigned long long *lohi;  // bit patterns of lo, hi (divergence.jl:92)
+    int dp, m;             // padded dimension; exponent m = 4*alpha
 };
 
 // q^M with a fixed multiplication chain (binary powering), M = 4*alpha in 1..40
@@ -514,17 +519,32 @@ const void *fp_kernel_part0(int m, int directed);
 const void *fp_kernel_part1(int m, int directed);
 const void *fp_kernel_part2(int m, int directed);
 const void *fp_kernel_part3(int m, int directed);
+const void *fp_kernel_part4(int m, int directed);
+const void *fp_kernel_part5(int m, int directed);
+const void *fp_kernel_part6(int m, int directed);
+const void *fp_kernel_part7(int m, int directed);
 // the same fixed point with the matrix streamed by cp.async.bulk through a shared-memory ring
 const void *fp_ring_kernel(int m, int directed);
 const void *fp_ring_kernel_part0(int m, int directed);
 const void *fp_ring_kernel_part1(int m, int directed);
 const void *fp_ring_kernel_part2(int m, int directed);
 const void *fp_ring_kernel_part3(int m, int directed);
+const void *fp_ring_kernel_part4(int m, int directed);
+const void *fp_ring_kernel_part5(int m, int directed);
+const void *fp_ring_kernel_part6(int m, int directed);
+const void *fp_ring_kernel_part7(int m, int directed);
 size_t fp_ring_smem_bytes(int directed);
+// recompute regime (cge_recompute.cu): kind as in launch_tiles, exponent taken from a.m
+void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+const void *fp_kernel_rc(int directed);
 int fp_ring_threads();
 void launch_tiles_part0(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part1(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part2(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part3(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part4(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part5(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part6(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+void launch_tiles_part7(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 
 }  // namespace cge

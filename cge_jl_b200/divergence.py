@@ -168,7 +168,7 @@ def _check(rc):
 
 
 def make_problem(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
-                 init_embed, split, directed, samples, max_alphas=0, driver=0):
+                 init_embed, split, directed, samples, max_alphas=0, driver=0, regime=0):
     """Fill a ``cge_b200_problem`` from reference-style (1-based) arrays.
 
     Returns ``(problem, keep)``; ``keep`` holds the arrays the struct points into.
@@ -205,13 +205,13 @@ def make_problem(edges, eweights, comm, embed, distances, vweights, init_vweight
         p.n_sets, p.n_samples = pi.shape
         p.pos_i, p.pos_j, p.pos_w, p.neg_i, p.neg_j = _pi(pi), _pi(pj), _pd(pw), _pi(ni), _pi(nj)
         keep += [pi, pj, pw, ni, nj]
-    p.max_alphas, p.driver = int(max_alphas), int(driver)
+    p.max_alphas, p.driver, p.regime = int(max_alphas), int(driver), int(regime)
     return p, keep
 
 
 def _score(directed, edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
            init_edges, init_eweights, init_embed, split, seed, auc_samples, verbose, samples,
-           return_stats, max_alphas, driver, scorer):
+           return_stats, max_alphas, driver, scorer, regime=0):
     edges = _i64(edges)
     no_vertices = int(edges.max())                      # divergence.jl:41
     no_edges = edges.shape[0]
@@ -241,7 +241,7 @@ def _score(directed, edges, eweights, comm, embed, distances, vweights, init_vwe
                                  init_vweights if landmarks else None,
                                  v_to_l if landmarks else None,
                                  init_embed if landmarks else None, split, directed, samples,
-                                 max_alphas, driver)
+                                 max_alphas, driver, regime)
     own = scorer is None
     sc = Scorer() if own else scorer
     try:
@@ -258,7 +258,7 @@ def _score(directed, edges, eweights, comm, embed, distances, vweights, init_vwe
 
 def wGCL(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l, init_edges,
          init_eweights, init_embed, split, seed=-1, auc_samples=10000, verbose=False, *,
-         samples=None, return_stats=False, max_alphas=0, driver=0, scorer=None):
+         samples=None, return_stats=False, max_alphas=0, driver=0, scorer=None, regime=0):
     """Weighted Geometric Chung-Lu fit + global/local divergence (divergence.jl:27-257).
 
     Positional arguments and the returned ``[best_alpha, best_div, best_div_ext, best_div_int,
@@ -268,14 +268,14 @@ def wGCL(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_
     """
     return _score(False, edges, eweights, comm, embed, distances, vweights, init_vweights,
                   v_to_l, init_edges, init_eweights, init_embed, split, seed, auc_samples,
-                  verbose, samples, return_stats, max_alphas, driver, scorer)
+                  verbose, samples, return_stats, max_alphas, driver, scorer, regime)
 
 
 def wGCL_directed(edges, eweights, comm, embed, distances, vweights, init_vweights, v_to_l,
                   init_edges, init_eweights, init_embed, split, seed=-1, auc_samples=10000,
                   verbose=False, *, samples=None, return_stats=False, max_alphas=0, driver=0,
-                  scorer=None):
+                  scorer=None, regime=0):
     """Directed variant (divergence.jl:282-561); 6-element ``[-1,0,0,0,0,0]`` for a star graph."""
     return _score(True, edges, eweights, comm, embed, distances, vweights, init_vweights,
                   v_to_l, init_edges, init_eweights, init_embed, split, seed, auc_samples,
-                  verbose, samples, return_stats, max_alphas, driver, scorer)
+                  verbose, samples, return_stats, max_alphas, driver, scorer, regime)

@@ -49,6 +49,13 @@ enum {
     CGE_B200_DRIVER_RING = 3          /* same, matrix streamed by cp.async.bulk through a smem ring */
 };
 
+/* where the pair matrix lives */
+enum {
+    CGE_B200_REGIME_AUTO = 0,         /* stored when it fits in free HBM, else recompute */
+    CGE_B200_REGIME_STORED = 1,       /* q = (1-D)^(1/4) kept in HBM: 8 B per pair and pass, HBM bound */
+    CGE_B200_REGIME_RECOMPUTE = 2     /* distances re-derived from the embedding every pass: FP64 bound */
+};
+
 /*
  * One scoring problem = the argument list of wGCL / wGCL_directed.
  * Index arrays hold `index_base`-based ids (1 when passed straight from Julia).
@@ -94,6 +101,8 @@ typedef struct cge_b200_problem {
     /* tuning; 0 = default */
     int32_t max_alphas;           /* evaluate only the first max_alphas grid points (<= 40) */
     int32_t driver;               /* CGE_B200_DRIVER_* */
+    int32_t regime;               /* CGE_B200_REGIME_* */
+    int32_t reserved;
 } cge_b200_problem;
 
 /* filled by run()/score(); everything a roofline computation or a parity test needs */
@@ -110,6 +119,7 @@ typedef struct cge_b200_stats {
     int64_t matrix_bytes;                   /* bytes of the stored q matrix */
     int64_t launches;                       /* kernels launched by this library in the call */
     int32_t n_tiles, grid, driver, n_ranks;
+    int32_t regime, reserved;               /* regime actually used */
     float ms_upload;                        /* H2D + host preprocessing */
     float ms_build;                         /* distance tiles + normalisation (CUDA events) */
     float ms_solve;                         /* the alpha loop (CUDA events) */

@@ -37,7 +37,7 @@ struct Problem
     init_row_stride::Int64; init_col_stride::Int64
     n_samples::Int64; n_sets::Int64
     pos_i::Ptr{Int64}; pos_j::Ptr{Int64}; pos_w::Ptr{Float64}; neg_i::Ptr{Int64}; neg_j::Ptr{Int64}
-    max_alphas::Int32; driver::Int32
+    max_alphas::Int32; driver::Int32; regime::Int32; reserved::Int32
 end
 
 # mirrors `cge_b200_stats`
@@ -46,11 +46,11 @@ mutable struct Stats
     iters::NTuple{N_ALPHA,Int32}; div::NTuple{N_ALPHA,Float64}; auc::NTuple{N_ALPHA,Float64}
     lo::Float64; hi::Float64; hi_full::Float64
     n::Int64; n_pairs::Int64; fp_sweeps::Int64; b_sweeps::Int64; matrix_bytes::Int64; launches::Int64
-    n_tiles::Int32; grid::Int32; driver::Int32; n_ranks::Int32
+    n_tiles::Int32; grid::Int32; driver::Int32; n_ranks::Int32; regime::Int32; reserved::Int32
     ms_upload::Float32; ms_build::Float32; ms_solve::Float32; ms_total::Float32
     ms_sweeps::Float32; ms_bsweeps::Float32
     Stats() = new(0, 0, ntuple(_ -> Int32(0), N_ALPHA), ntuple(_ -> NaN, N_ALPHA),
-                  ntuple(_ -> NaN, N_ALPHA), 0.0, 0.0, 0.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                  ntuple(_ -> NaN, N_ALPHA), 0.0, 0.0, 0.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
                   0f0, 0f0, 0f0, 0f0, 0f0, 0f0)
 end
 
@@ -149,7 +149,7 @@ function score(directed::Bool, edges, eweights, comm, embed, distances, vweights
                     lm ? pointer(init_embed) : C_NULL, 1, lm ? size(init_embed, 1) : 0,
                     auc_samples, size(pos_i, 2),
                     pointer(pos_i), pointer(pos_j), pointer(pos_w), pointer(neg_i), pointer(neg_j),
-                    0, 0)
+                    0, 0, 0, 0)
         rc = ccall((:cge_b200_score, LIB), Cint,
                    (Ref{Problem}, Ptr{Float64}, Ref{Int32}, Ref{Stats}), p, out, out_len, stats)
         check(rc)

@@ -16,7 +16,7 @@ README_GOLDEN = [6.25, 0.002961243353776198]  # /root/reference/README.md:99, el
 
 
 def run_pair(scorer, directed, edges, ew, comm, emb, dist, vw, lm_args=None, split=False,
-             seed=42, K=2000, samples="draw", driver=0):
+             seed=42, K=2000, samples="draw", driver=0, regime=0):
     """Score on the GPU and with the oracle using the same sampled pairs."""
     if lm_args is None:
         init_vw, v2l, init_edges, init_ew, init_emb = EMPTY
@@ -29,8 +29,9 @@ def run_pair(scorer, directed, edges, ew, comm, emb, dist, vw, lm_args=None, spl
     f_gpu = dv.wGCL_directed if directed else dv.wGCL
     out, stats = f_gpu(edges, ew, comm, emb, dist, vw, init_vw, v2l, init_edges, init_ew,
                        init_emb, split, seed, K, False, samples=samples, return_stats=True,
-                       scorer=scorer, driver=driver)
-    assert driver == 0 or stats.driver == driver
+                       scorer=scorer, driver=driver, regime=regime)
+    assert driver == 0 or stats.driver == driver or regime == 2
+    assert stats.regime == (regime or 1)
     f_ref = oracle.wgcl_directed if directed else oracle.wgcl
     ref, tr = f_ref(edges, ew, comm, emb, dist, vw, init_vw if lm_args else None,
                     v2l if lm_args else None, init_emb if lm_args else None, split, samples)
@@ -135,6 +136,33 @@ def test_synthetic_multi_tile(scorer, directed, n, k, d, driver):
                                                  weighted=True)
     out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw, K=3000,
                                    driver=driver)
+    assert_parity(out, stats, ref, tr)
+
+
+@pytest.mark.parametrize("driver", [1, 2], ids=["hostloop", "persistent"])
+@pytest.mark.parametrize("directed,n,k,d", [(False, 115, 0, 0), (True, 115, 0, 0),
+                                            (False, 700, 5, 20), (True, 520, 7, 33)])
+def test_recompute_regime(scorer, directed, n, k, d, driver):
+    """No stored matrix: distances are re-derived from the embedding in every pass (north_star
+    kernel (a)); same parity bars against the oracle as the stored regime."""
+    if k == 0:
+        edges, ew, vw, comm, emb = load_fixture("test115_weighted.npz" if directed else "test115.npz")
+    else:
+        edges, ew, vw, comm, emb = planted_partition(n, k, d, seed=n + k, directed=directed,
+                                                     weighted=True)
+    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
+                                   driver=driver, regime=2)
+    assert stats.matrix_bytes == 0
+    assert_parity(out, stats, ref, tr)
+
+
+def test_recompute_regime_landmarks_with_diagonal(scorer):
+    """Landmark mode has a non-zero diagonal (d_ii) and lo > 0 possible: recompute vs stored."""
+    edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    dii, lemb, lcomm, ledges, lw, lweight, v2l = landmarks(
+        edges, ew, vw, clusters_of(comm), comm, emb, False, 20, 1, split_cluster_rss, False)
+    out, stats, ref, tr = run_pair(scorer, False, ledges, lw, lcomm, lemb, dii, lweight,
+                                   lm_args=(vw, v2l, edges, ew, emb), regime=2)
     assert_parity(out, stats, ref, tr)
 
 
