@@ -156,6 +156,10 @@ def run_b200(args):
         ids = [dv.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         sc.comm_init(ids[0], rank, world)
+        if not args.no_p2p:  # per-pass exchange over NVLink peer memory inside the kernel
+            handles = [None] * world
+            dist.all_gather_object(handles, sc.p2p_export(w["n"]))
+            sc.p2p_import(handles)
     problem, keep = dv.make_problem(w["edges"], w["ew"], w["comm"], w["emb"], np.zeros(n), w["vw"],
                                     None, None, None, False, False, w["samples"], 0, args.driver,
                                     args.regime)
@@ -282,6 +286,9 @@ def main():
                     help="alpha values per CPU sample (bounds the CPU baseline's run time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--no-p2p", action="store_true",
+                    help="multi-GPU: NCCL all-reduce per pass from the host instead of the "
+                         "in-kernel NVLink exchange")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -65,7 +65,8 @@ EXPORTS = [
     "cge_b200_version", "cge_b200_device_count", "cge_b200_last_error", "cge_b200_score",
     "cge_b200_create", "cge_b200_destroy", "cge_b200_upload", "cge_b200_run",
     "cge_b200_comm_id_size", "cge_b200_comm_unique_id", "cge_b200_comm_init",
-    "cge_b200_shard_plan", "cge_b200_debug_read",
+    "cge_b200_shard_plan", "cge_b200_debug_read", "cge_b200_p2p_handle_size",
+    "cge_b200_p2p_export", "cge_b200_p2p_import",
 ]
 
 _lib = None
@@ -96,6 +97,9 @@ def load():
     lib.cge_b200_comm_unique_id.argtypes = [vp]
     lib.cge_b200_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     lib.cge_b200_shard_plan.argtypes = [C.c_int64, C.c_int, C.c_int, _pi, _pi, _pi]
+    lib.cge_b200_p2p_handle_size.restype = C.c_int
+    lib.cge_b200_p2p_export.argtypes = [vp, C.c_int64, vp]
+    lib.cge_b200_p2p_import.argtypes = [vp, vp]
     lib.cge_b200_debug_read.argtypes = [vp, C.c_int, _pd, C.c_int64]
     _lib = lib
     return lib

@@ -481,6 +481,12 @@ struct cge_b200_handle {
     // multi-rank
     int rank = 0, n_ranks = 1;
     void *nccl_comm = nullptr;
+    // NVLink peer exchange (optional)
+    void *xbuf = nullptr;           // own exchange allocation
+    void *xpeer[8] = {nullptr};     // every rank's allocation as mapped here
+    int64_t xcap = 0;               // vertex capacity of a slot
+    bool p2p_ready = false;
+    unsigned pass_total = 0;        // fixed-point passes executed with the exchange so far
     // host copies
     std::vector<int64_t> perm;           // sorted position -> caller's 0-based vertex
     std::vector<double> C;               // k*k observed community mass (divergence.jl:55-63/337-345)
@@ -828,8 +834,12 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     S.n_pairs = h->n * (h->n + 1) / 2;
     S.n_ranks = h->n_ranks;
     // the persistent kernel cannot call NCCL between passes: multi-rank runs use the host loop
+    const bool can_p2p = h->n_ranks > 1 && h->p2p_ready && h->np <= h->xcap &&
+                         h->regime == CGE_B200_REGIME_STORED;
     const int driver =
-        h->n_ranks > 1 ? CGE_B200_DRIVER_HOSTLOOP
+        h->n_ranks > 1 ? ((can_p2p && h->driver != CGE_B200_DRIVER_HOSTLOOP)
+                              ? CGE_B200_DRIVER_PERSISTENT
+                              : CGE_B200_DRIVER_HOSTLOOP)
         : h->driver == CGE_B200_DRIVER_AUTO
             ? CGE_B200_DRIVER_PERSISTENT  // measured: 65.3 us/pass vs 72.2 for the TMA ring (r01)
             : h->driver;
@@ -962,6 +972,17 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     }
     A.out_iters = reinterpret_cast<int *>(h->fpres.as<char>());
     A.out_diff = reinterpret_cast<double *>(h->fpres.as<char>() + 8);
+    A.rank = h->rank;
+    A.n_ranks = (driver == CGE_B200_DRIVER_PERSISTENT && h->n_ranks > 1) ? h->n_ranks : 1;
+    A.xcap = h->xcap;
+    for (int r = 0; r < 8; ++r) {
+        A.xbuf_peer[r] = reinterpret_cast<double *>(h->xpeer[r]);
+        A.flag_peer[r] = h->xpeer[r] ? reinterpret_cast<unsigned *>(
+                                           static_cast<char *>(h->xpeer[r]) +
+                                           (size_t)2 * h->n_ranks * 2 * (size_t)h->xcap * 8)
+                                     : nullptr;
+    }
+    A.pass_base = h->pass_total;
     A.emb = h->emb.as<double>();
     A.diag = h->dist.as<double>();
     A.lohi = lohi;
@@ -1016,6 +1037,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             const int want = std::max(local_tiles, (n + 31) / 32);
             const int cgrid = std::max(1, std::min(want, bps * h->sm_count));
             A.eps0 = eps;
+            A.pass_base = h->pass_total;
             CUDA_TRY(cudaMemsetAsync(h->slots.p, 0, 64, st));
             void *kargs[] = {(void *)&A};
             cudaEventRecord(h->next_event(), st);
@@ -1123,6 +1145,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             std::memcpy(&it, pin, 4);
             std::memcpy(&diff, pin + 8, 8);
             S.fp_sweeps += it;
+            if (A.n_ranks > 1) h->pass_total += (unsigned)it;
             if (it >= A.max_iter)
                 return fail(CGE_B200_ERR_STATE, "fixed point did not converge in 200000 passes");
         }
@@ -1245,6 +1268,9 @@ void cge_b200_destroy(cge_b200_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+    for (int r = 0; r < 8; ++r)
+        if (h->xpeer[r] && h->xpeer[r] != h->xbuf) cudaIpcCloseMemHandle(h->xpeer[r]);
+    if (h->xbuf) cudaFree(h->xbuf);
     for (DevBuf *b :
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
@@ -1308,6 +1334,46 @@ int cge_b200_comm_init(cge_b200_handle *h, const void *id_bytes, int rank, int n
     h->rank = rank;
     h->n_ranks = n_ranks;
     h->uploaded = false;
+    return 0;
+}
+
+int cge_b200_p2p_handle_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+
+int cge_b200_p2p_export(cge_b200_handle *h, int64_t max_vertices, void *handle_out) {
+    if (!h || !handle_out || max_vertices <= 0) return fail(CGE_B200_ERR_ARG, "bad p2p_export argument");
+    if (h->n_ranks < 2 || h->n_ranks > 8)
+        return fail(CGE_B200_ERR_STATE, "p2p exchange needs comm_init with 2..8 ranks first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->xbuf) {
+        cudaFree(h->xbuf);
+        h->xbuf = nullptr;
+    }
+    h->p2p_ready = false;
+    h->xcap = (max_vertices + TILE - 1) / TILE * TILE;
+    const size_t bytes = (size_t)2 * h->n_ranks * 2 * (size_t)h->xcap * 8 + 256;
+    CUDA_TRY(cudaMalloc(&h->xbuf, bytes));
+    CUDA_TRY(cudaMemset(h->xbuf, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t *>(handle_out), h->xbuf));
+    return 0;
+}
+
+int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles) {
+    if (!h || !all_handles) return fail(CGE_B200_ERR_ARG, "bad p2p_import argument");
+    if (!h->xbuf) return fail(CGE_B200_ERR_STATE, "p2p_import before p2p_export");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const cudaIpcMemHandle_t *hs = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+    for (int r = 0; r < h->n_ranks; ++r) {
+        if (r == h->rank) {
+            h->xpeer[r] = h->xbuf;
+        } else {
+            void *ptr = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&ptr, hs[r], cudaIpcMemLazyEnablePeerAccess));
+            h->xpeer[r] = ptr;
+        }
+    }
+    h->pass_total = 0;
+    h->p2p_ready = true;
     return 0;
 }
 

@@ -54,7 +54,22 @@ struct SweepArgs {
     const double *diag;    // [np] D_ii (divergence.jl:85-86)
     const unsigned long long *lohi;  // bit patterns of lo, hi (divergence.jl:92)
     int dp, m;             // padded dimension; exponent m = 4*alpha
+    // multi-GPU persistent driver: per-pass exchange of the raw degree sums over NVLink peer memory
+    int rank, n_ranks;     // n_ranks == 1: no exchange
+    unsigned pass_base;    // passes completed before this launch (flags only grow)
+    long long xcap;        // vertex capacity of one exchange slot
+    double *xbuf_peer[8];  // rank r's exchange buffer [2 parities][n_ranks writers][2][xcap], peer-mapped
+    unsigned *flag_peer[8];  // rank r's arrival flags [n_ranks]
 };
+
+__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // q^M with a fixed multiplication chain (binary powering), M = 4*alpha in 1..40
 template <int M>
@@ -417,6 +432,37 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_bsweep(const __grid_constant__ 
     }
 }
 
+// divergence.jl:160-165 (undirected) / 451-461 with the doubled diagonal of :442-447 (directed)
+// for vertex v given the summed raw degree sums; returns the vertex's residual.
+template <int M, bool DIRECTED>
+__device__ __forceinline__ double fp_update(const SweepArgs &a, int v, double sa, double sb,
+                                            double eps) {
+    double e = 0.0;
+    if (!DIRECTED) {
+        const double t = __ldcg(a.Ta + v), wv = a.w_a[v];
+        const double s = t * sa;
+        a.Tw_a[v] = t + eps * t * (wv / s - 1.0);
+        a.S_a[v] = s;
+        e = fabs(wv - s);
+    } else {
+        const double ti = __ldcg(a.Ta + v), to = __ldcg(a.Tb + v);
+        const double gd = powm<M>(a.qdiag[v]);
+        const double sin = ti * (sa + to * gd), sout = to * (sb + ti * gd);
+        a.S_a[v] = sin;
+        a.S_b[v] = sout;
+        const double di = a.w_a[v], dout = a.w_b[v];
+        if (di > 0.0) {
+            a.Tw_a[v] = ti + eps * ti * (di / sin - 1.0);
+            e = fmax(e, fabs(di - sin));
+        }
+        if (dout > 0.0) {
+            a.Tw_b[v] = to + eps * to * (dout / sout - 1.0);
+            e = fmax(e, fabs(dout - sout));
+        }
+    }
+    return e;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Persistent fixed point of one alpha (divergence.jl:150-168 / 434-467) as ONE cooperative
 // launch: every pass is [tiles] -> grid.sync -> [reduce partials, update T, residual] ->
@@ -445,8 +491,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
         }
         grid.sync();
         // 32 vertices per CTA step: warp w sums the partial slots b = w, w+8, ..., warp 0 adds
-        // the eight sub-sums in fixed order and applies divergence.jl:160-165 / 451-461
+        // the eight sub-sums in fixed order.  Single GPU: warp 0 applies divergence.jl:160-165 /
+        // 451-461 at once.  Multi GPU: the sums of this rank's tiles go to every rank's exchange
+        // buffer over NVLink (plain peer stores), one release flag per peer announces them, and
+        // every rank adds the n_ranks contributions in rank order -- identical T on all ranks,
+        // no host round trip, no separate collective.
         double e = 0.0;
+        const bool multi = a.n_ranks > 1;
+        const unsigned pass_no = a.pass_base + (unsigned)it + 1u;
+        const size_t xpar = (size_t)(pass_no & 1u) * a.n_ranks;
         for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
             const int v = g * 32 + lane;
             double pa = 0.0, pb = 0.0;
@@ -466,35 +519,49 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
                     sa += s_red[w2 * 32 + lane];
                     if (DIRECTED) sb += s_red[NWARPS * 32 + w2 * 32 + lane];
                 }
-                if (!DIRECTED) {
-                    const double t = __ldcg(a.Ta + v), wv = a.w_a[v];
-                    const double s = t * sa;
-                    a.Tw_a[v] = t + eps * t * (wv / s - 1.0);
-                    a.S_a[v] = s;
-                    e = fmax(e, fabs(wv - s));
+                if (multi) {
+                    const size_t o = ((xpar + a.rank) * 2) * (size_t)a.xcap + v;
+                    for (int r = 0; r < a.n_ranks; ++r) {
+                        a.xbuf_peer[r][o] = sa;
+                        if (DIRECTED) a.xbuf_peer[r][o + a.xcap] = sb;
+                    }
                 } else {
-                    const double ti = __ldcg(a.Ta + v), to = __ldcg(a.Tb + v);
-                    const double gd = powm<M>(a.qdiag[v]);
-                    const double sin = ti * (sa + to * gd), sout = to * (sb + ti * gd);
-                    a.S_a[v] = sin;
-                    a.S_b[v] = sout;
-                    const double di = a.w_a[v], dout = a.w_b[v];
-                    if (di > 0.0) {
-                        a.Tw_a[v] = ti + eps * ti * (di / sin - 1.0);
-                        e = fmax(e, fabs(di - sin));
-                    }
-                    if (dout > 0.0) {
-                        a.Tw_b[v] = to + eps * to * (dout / sout - 1.0);
-                        e = fmax(e, fabs(dout - sout));
-                    }
+                    e = fmax(e, fp_update<M, DIRECTED>(a, v, sa, sb, eps));
                 }
             }
             __syncthreads();
         }
-        if (w == 0) {
+        if (multi) {
+            __threadfence_system();
+            grid.sync();  // every peer store of this rank is issued and fenced
+            if (blockIdx.x == 0 && (int)threadIdx.x < a.n_ranks)
+                st_release_sys_u32(a.flag_peer[threadIdx.x] + a.rank, pass_no);
+            if (threadIdx.x == 0) {
+                for (int r = 0; r < a.n_ranks; ++r) {
+                    unsigned spins = 0;
+                    while ((int)(ld_acquire_sys_u32(a.flag_peer[a.rank] + r) - pass_no) < 0)
+                        if (++spins > (1u << 26)) __trap();  // a lost peer must not hang the GPU
+                }
+            }
+            __syncthreads();
+            const double *mine = a.xbuf_peer[a.rank];
+            for (int g = blockIdx.x * NWARPS + w; g < ngroups; g += gridDim.x * NWARPS) {
+                const int v = g * 32 + lane;
+                if (v < a.n) {
+                    double sa = 0.0, sb = 0.0;
+                    for (int r = 0; r < a.n_ranks; ++r) {
+                        const size_t o = ((xpar + r) * 2) * (size_t)a.xcap + v;
+                        sa += __ldcg(mine + o);
+                        if (DIRECTED) sb += __ldcg(mine + o + a.xcap);
+                    }
+                    e = fmax(e, fp_update<M, DIRECTED>(a, v, sa, sb, eps));
+                }
+            }
+        }
+        if (w == 0 || multi) {  // max is order independent: one atomic per contributing warp
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) e = fmax(e, __shfl_xor_sync(FULL, e, off));
-            if (lane == 0)
+            if (lane == 0 && e > 0.0)
                 atomicMax(a.slots + it % 3, (unsigned long long)__double_as_longlong(e));
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) a.slots[(it + 1) % 3] = 0ull;

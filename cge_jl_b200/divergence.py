@@ -132,6 +132,16 @@ class Scorer:
         rc = self._lib.cge_b200_comm_init(self._h, C.cast(buf, C.c_void_p), rank, n_ranks)
         _check(rc)
 
+    def p2p_export(self, max_vertices):
+        buf = C.create_string_buffer(self._lib.cge_b200_p2p_handle_size())
+        _check(self._lib.cge_b200_p2p_export(self._h, int(max_vertices), C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def p2p_import(self, handles):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(self._lib.cge_b200_p2p_import(self._h, C.cast(buf, C.c_void_p)))
+
     def upload(self, problem, keep):
         self._keep = keep
         _check(self._lib.cge_b200_upload(self._h, C.byref(problem)))

@@ -156,6 +156,17 @@ int cge_b200_comm_id_size(void);
 int cge_b200_comm_unique_id(void *id_bytes);
 int cge_b200_comm_init(cge_b200_handle *h, const void *id_bytes, int rank, int n_ranks);
 
+/* Optional NVLink peer-memory exchange for the multi-GPU persistent driver: instead of one NCCL
+ * all-reduce per pass issued by the host, the fixed-point kernel itself stores its partial degree
+ * sums into every peer's exchange buffer and synchronises with release/acquire flags, so a whole
+ * alpha runs in one launch on every rank.  After comm_init: every rank calls p2p_export (allocates
+ * its buffer for up to max_vertices vertices, returns a 64-byte CUDA IPC handle), the caller
+ * all-gathers the handles, every rank calls p2p_import with the n_ranks x 64 bytes.  Without it
+ * multi-rank runs fall back to the NCCL host loop. */
+int cge_b200_p2p_handle_size(void);
+int cge_b200_p2p_export(cge_b200_handle *h, int64_t max_vertices, void *handle_out);
+int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles);
+
 /* Host-only: the tile range [*tile_begin, *tile_end) of the upper-triangular tile sequence
  * that `rank` of `n_ranks` owns for an n-vertex problem, and the tile count. No GPU needed. */
 int cge_b200_shard_plan(int64_t n, int rank, int n_ranks, int64_t *n_tiles,

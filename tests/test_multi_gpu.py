@@ -26,7 +26,7 @@ def _problem(directed):
     return n, edges, ew, vw, comm, emb
 
 
-def _worker(rank, world, port, directed, q):
+def _worker(rank, world, port, directed, p2p, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -40,6 +40,10 @@ def _worker(rank, world, port, directed, q):
     ids = [dv.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     sc.comm_init(ids[0], rank, world)
+    if p2p:  # NVLink peer exchange inside the persistent kernel instead of NCCL per pass
+        handles = [None] * world
+        dist.all_gather_object(handles, sc.p2p_export(n))
+        sc.p2p_import(handles)
     p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False,
                               directed, samples)
     sc.upload(p, keep)
@@ -51,8 +55,9 @@ def _worker(rank, world, port, directed, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("p2p", [False, True], ids=["nccl-hostloop", "nvlink-persistent"])
 @pytest.mark.parametrize("directed", [False, True])
-def test_two_gpu_matches_one_gpu_and_oracle(directed):
+def test_two_gpu_matches_one_gpu_and_oracle(directed, p2p):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -65,14 +70,14 @@ def test_two_gpu_matches_one_gpu_and_oracle(directed):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, directed, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, directed, p2p, q)) for r in range(2)]
     for p in procs:
         p.start()
     out2, iters2, div2, auc2, n_ranks, driver = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert n_ranks == 2 and driver == 1
+    assert n_ranks == 2 and driver == (2 if p2p else 1)
     n, edges, ew, vw, comm, emb = _problem(directed)
     samples = dv.draw_samples(edges, ew, n, 2000, 42, directed, True)
     f = dv.wGCL_directed if directed else dv.wGCL
