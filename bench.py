@@ -230,9 +230,27 @@ def run_b200(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    bytes_per_launch = 8.0 * pairs / world          # algorithmic: 8 B per unordered pair per pass
-    avg_launch_s = 1e-3 * sweep_ms / max(sweeps, 1)
+    # dominant kernel: the fixed point.  Persistent drivers: one launch per alpha runs all its
+    # passes; host loop: one launch per pass.  Algorithmic bytes = 8 B per unordered pair and pass.
+    persistent = int(stats.driver) in (2, 3)
+    fp_launches = (a_run if persistent else int(stats.fp_sweeps)) * args.steps
+    passes_per_launch = sweeps / max(fp_launches, 1)
+    bytes_per_launch = 8.0 * pairs / world * passes_per_launch
+    avg_launch_s = 1e-3 * sweep_ms / max(fp_launches, 1)
     achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if world == 1 and tr["workload_pairs"] == pairs and int(stats.regime) == 1:
+            traffic = (tr["dram_bytes_per_pass"] * passes_per_launch if persistent
+                       else tr["hostloop_k_sweep_bytes_per_launch"])
+    except Exception:
+        pass
+    kname = {1: "k_sweep<M,false> (one fixed-point pass per launch)",
+             2: "k_fixed_point<M,false> (all passes of one alpha per cooperative launch)",
+             3: "k_fixed_point_ring<M,false> (all passes of one alpha, cp.async.bulk ring)"}
+    if int(stats.regime) == 2:
+        kname = {1: "k_sweep_rc<false>", 2: "k_fixed_point_rc<false>", 3: "k_fixed_point_rc<false>"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt_res / args.steps,
@@ -256,10 +274,14 @@ def run_b200(args):
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * dt_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None,
-                     "kernel": "k_sweep<M,false> (fixed-point pass over the stored q matrix)",
-                     "bytes_per_launch": bytes_per_launch,
-                     "avg_launch_us": 1e6 * avg_launch_s, "launches_timed": int(sweeps),
+                     "frac": achieved / peak if peak else None, "traffic": traffic,
+                     "kernel": kname.get(int(stats.driver), "?"),
+                     "bytes_per_launch": bytes_per_launch, "avg_launch_us": 1e6 * avg_launch_s,
+                     "passes_per_launch": passes_per_launch,
+                     "avg_pass_us": 1e6 * avg_launch_s / max(passes_per_launch, 1e-9),
+                     "launches_timed": int(fp_launches),
+                     "note": "achieved = 8 B x unordered pairs x passes in the launch / CUDA-event "
+                             "duration of the launch, events recorded by the library on its stream",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"
                                     if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
     }
