@@ -244,16 +244,19 @@ __device__ __forceinline__ void block_max_to_slot(double e, unsigned long long *
 // sum of the per-block partial slots in fixed order: a CTA takes 32 vertices, warp w adds the
 // slots b = w, w+8, ... (coalesced 256-byte rows), warp 0 adds the eight sub-sums
 __global__ void __launch_bounds__(NTHREADS)
-k_reduce_part(const double *__restrict__ part, int nb, int np, int n, double *__restrict__ sraw) {
+k_reduce_part(const SweepArgs a, const double *__restrict__ part, double *__restrict__ sraw) {
     __shared__ double s_red[NWARPS * 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int v = blockIdx.x * 32 + lane;
     double p = 0.0;
-    if (v < n)
-        for (int b = w; b < nb; b += NWARPS) p += __ldcg(part + (size_t)b * np + v);
+    if (v < a.n) {
+        int b_lo, b_hi;
+        part_range(a, v, b_lo, b_hi);
+        for (int b = b_lo + w; b < b_hi; b += NWARPS) p += __ldcg(part + (size_t)b * a.np + v);
+    }
     s_red[w * 32 + lane] = p;
     __syncthreads();
-    if (w == 0 && v < n) {
+    if (w == 0 && v < a.n) {
         double s = 0.0;
 #pragma unroll
         for (int w2 = 0; w2 < NWARPS; ++w2) s += s_red[w2 * 32 + lane];
@@ -947,6 +950,15 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     A.tile_ij = h->tile_ij.as<int2>();
     A.tile_begin = tb;
     A.tile_end = te;
+    {   // tile rows covered by [tb, te): row bi starts at tile bi*nb - bi(bi-1)/2
+        auto row_of = [&](long long t) {
+            int bi = 0;
+            while (bi + 1 < nb && tile_index(nb, bi + 1, bi + 1) <= t) ++bi;
+            return bi;
+        };
+        A.row_begin = te > tb ? row_of(tb) : 0;
+        A.row_end = te > tb ? row_of(te - 1) : -1;
+    }
     A.nb = nb; A.np = np; A.n = n; A.k = k;
     A.Ta = h->Ta.as<double>();
     A.Tb = h->Tb.as<double>();
@@ -1058,11 +1070,10 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 h->ev_is_b.push_back(0);
                 ++h->launches;
             }
-            k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A.partA, nb, np, n,
-                                                              h->sraw_a.as<double>());
+            k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A, A.partA, h->sraw_a.as<double>());
             ++h->launches;
             if (h->directed) {
-                k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A.partB, nb, np, n,
+                k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A, A.partB,
                                                                   h->sraw_b.as<double>());
                 ++h->launches;
             }

@@ -30,6 +30,7 @@ struct SweepArgs {
     const double *q;       // this rank's tiles: global tile t at q + (t - tile_begin) * TILE_ELEMS
     const int2 *tile_ij;   // [n_tiles] (bi, bj) of every global tile
     long long tile_begin, tile_end;
+    int row_begin, row_end;  // tile rows bi touched by [tile_begin, tile_end)
     int nb, np, n, k;
     const double *Ta;      // undirected: T        directed: Tin
     const double *Tb;      //                      directed: Tout
@@ -69,6 +70,16 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+// Partial slots part[b][v] that this rank's tiles can have written for vertex v (block bv):
+// row sums of tiles (bv, b >= bv) when bv is one of the rank's tile rows, column sums of tiles
+// (b, bv) for the rank's tile rows b < bv.  Everything else is still zero and is not read
+// (at 200k vertices on 8 GPUs this removes most of the 2.5 GB per pass the reduction would read).
+__device__ __forceinline__ void part_range(const SweepArgs &a, int v, int &lo, int &hi) {
+    const int bv = v / TILE;
+    lo = a.row_begin;
+    hi = (bv >= a.row_begin && bv <= a.row_end) ? a.nb : (bv > a.row_end ? a.row_end + 1 : a.row_begin);
 }
 
 // q^M with a fixed multiplication chain (binary powering), M = 4*alpha in 1..40
@@ -504,7 +515,9 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
             const int v = g * 32 + lane;
             double pa = 0.0, pb = 0.0;
             if (v < a.n) {
-                for (int b = w; b < a.nb; b += NWARPS) {
+                int b_lo, b_hi;
+                part_range(a, v, b_lo, b_hi);
+                for (int b = b_lo + w; b < b_hi; b += NWARPS) {
                     pa += __ldcg(a.partA + (size_t)b * a.np + v);
                     if (DIRECTED) pb += __ldcg(a.partB + (size_t)b * a.np + v);
                 }

@@ -274,7 +274,9 @@ k_fixed_point_ring(const __grid_constant__ SweepArgs a) {
             const int v = g * 32 + lane;
             double pa = 0.0, pb = 0.0;
             if (v < a.n) {
-                for (int b = w; b < a.nb; b += NWARPS) {
+                int b_lo, b_hi;
+                part_range(a, v, b_lo, b_hi);
+                for (int b = b_lo + w; b < b_hi; b += NWARPS) {
                     pa += __ldcg(a.partA + (size_t)b * a.np + v);
                     if (DIRECTED) pb += __ldcg(a.partB + (size_t)b * a.np + v);
                 }
