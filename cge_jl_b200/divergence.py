@@ -47,6 +47,21 @@ def _sample_non_edges(rng, n, codes_sorted, K, directed):
     unordered i<j (ordered i!=j when directed) that are not in the edge set.  The reference
     materialises NE and indexes it; rejection sampling draws from the same distribution without
     the O(n^2) array."""
+    n_pairs = n * (n - 1) if directed else n * (n - 1) // 2
+    ci, cj = codes_sorted // (n + 1), codes_sorted % (n + 1)
+    n_ne = n_pairs - int(np.count_nonzero(ci != cj))
+    if n_ne <= 0:
+        raise ValueError("collection must be non-empty: the graph has no non-edges to sample "
+                         "(divergence.jl:137 leaves NE empty)")
+    if n_ne * 8 < n_pairs and n <= 5000:
+        # dense graph: rejection would spin; enumerate NE like the reference does
+        ii, jj = np.meshgrid(np.arange(1, n + 1), np.arange(1, n + 1), indexing="ij")
+        keep = (ii != jj) if directed else (ii < jj)
+        ii, jj = ii[keep], jj[keep]
+        code = ii * (n + 1) + jj
+        free = ~np.isin(code, codes_sorted)
+        pick = rng.integers(0, int(free.sum()), size=K)
+        return ii[free][pick], jj[free][pick]
     out_i = np.empty(K, dtype=np.int64)
     out_j = np.empty(K, dtype=np.int64)
     got = 0
@@ -58,9 +73,10 @@ def _sample_non_edges(rng, n, codes_sorted, K, directed):
             i, j = np.minimum(i, j), np.maximum(i, j)
         ok = i != j
         code = i * (n + 1) + j
-        pos = np.searchsorted(codes_sorted, code)
-        pos[pos >= codes_sorted.shape[0]] = 0
-        ok &= codes_sorted[pos] != code if codes_sorted.size else True
+        if codes_sorted.size:
+            pos = np.searchsorted(codes_sorted, code)
+            pos[pos >= codes_sorted.shape[0]] = 0
+            ok &= codes_sorted[pos] != code
         i, j = i[ok][: K - got], j[ok][: K - got]
         out_i[got: got + i.shape[0]] = i
         out_j[got: got + i.shape[0]] = j

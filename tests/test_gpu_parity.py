@@ -222,3 +222,91 @@ def test_exact_10k_against_frozen_oracle(scorer, driver):
     assert_parity(out, stats, g["out"], Tr)
     assert int(stats.fp_sweeps) == 1026 and out[0] == 10.0  # SURVEY section 6 probe
     assert np.isclose(stats.lo, float(g["lo"])) and np.isclose(stats.hi, float(g["hi"]), rtol=1e-14)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases (the reference's tests cover none of these; the oracle defines the answer)
+# ---------------------------------------------------------------------------------------------
+def _tiny(n, edges, d=3, seed=0, k=2, w=None):
+    rng = np.random.default_rng(seed)
+    edges = np.asarray(edges, dtype=np.int64)
+    ew = np.ones(len(edges)) if w is None else np.asarray(w, dtype=np.float64)
+    vw = np.zeros(n)
+    np.add.at(vw, edges[:, 0] - 1, ew)
+    np.add.at(vw, edges[:, 1] - 1, ew)
+    comm = (np.arange(n) % k + 1).reshape(-1, 1)
+    return edges, ew, vw, comm, rng.normal(size=(n, d))
+
+
+@pytest.mark.parametrize("driver", [1, 2], ids=["hostloop", "persistent"])
+def test_tiny_graphs(scorer, driver):
+    """Three and four vertices: a single ragged tile, one community pair."""
+    for n, e in ((3, [[1, 2], [2, 3]]), (4, [[1, 2], [2, 3], [3, 4]])):
+        edges, ew, vw, comm, emb = _tiny(n, e)
+        out, stats, ref, tr = run_pair(scorer, False, edges, ew, comm, emb, np.zeros(n), vw, K=7,
+                                       driver=driver)
+        assert_parity(out, stats, ref, tr)
+
+
+def test_self_loops_multi_edges_and_single_sample(scorer):
+    """Self-loops stay in E (divergence.jl:131-134 keeps (i,i,w)), duplicate edges are sampled with
+    multiplicity, K = 1."""
+    e = [[1, 2], [2, 3], [3, 4], [4, 5], [5, 1], [2, 2], [1, 2], [3, 5]]
+    edges, ew, vw, comm, emb = _tiny(5, e, w=[1, 2, 1, 0.5, 1, 3, 1, 1])
+    for K in (1, 33):
+        out, stats, ref, tr = run_pair(scorer, False, edges, ew, comm, emb, np.zeros(5), vw, K=K)
+        assert_parity(out, stats, ref, tr)
+
+
+def test_duplicate_embedding_rows_and_isolated_vertex(scorer):
+    """Identical rows give D = 0 off the diagonal (q = 1); a vertex below max(edges) without
+    edges has weight 0 and its T decays (divergence.jl:162 with vweights[i] = 0)."""
+    edges, ew, vw, comm, emb = planted_partition(150, 3, 5, seed=9)
+    edges = edges[(edges[:, 0] != 7) & (edges[:, 1] != 7)]      # vertex 7 becomes isolated
+    ew = np.ones(edges.shape[0])
+    vw = np.zeros(150)
+    np.add.at(vw, edges[:, 0] - 1, ew)
+    np.add.at(vw, edges[:, 1] - 1, ew)
+    assert vw[6] == 0 and edges.max() == 150
+    emb[10] = emb[11] = emb[140]
+    out, stats, ref, tr = run_pair(scorer, False, edges, ew, comm, emb, np.zeros(150), vw, K=500)
+    assert_parity(out, stats, ref, tr)
+
+
+def test_directed_vertices_without_in_or_out_edges(scorer):
+    """Tin/Tout start at 0 where the degree is 0 and are never updated (divergence.jl:399-402,453,457)."""
+    e = [[1, 2], [1, 3], [2, 3], [3, 4], [4, 2], [5, 1], [5, 4], [2, 6]]
+    edges, ew, vw, comm, emb = _tiny(6, e, d=4, seed=3, w=[1, 1.5, 2, 1, 1, 0.7, 1, 1])
+    out, stats, ref, tr = run_pair(scorer, True, edges, ew, comm, emb, np.zeros(6), vw, K=50)
+    assert out.shape == (7,)
+    assert_parity(out, stats, ref, tr)
+
+
+def test_column_major_embedding_is_accepted_without_copy(scorer):
+    """Julia passes a column-major Matrix{Float64}; strides are part of the ABI."""
+    edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    samples = dv.draw_samples(edges, ew, 115, 300, 42, False, True)
+    a = dv.wGCL(edges, ew, comm, emb, np.zeros(115), vw, *EMPTY, False, 42, 300, False,
+                samples=samples, scorer=scorer)
+    emb_f = np.asfortranarray(emb)
+    assert emb_f.strides == (8, 8 * 115)
+    b = dv.wGCL(edges, ew, comm, emb_f, np.zeros(115), vw, *EMPTY, False, 42, 300, False,
+                samples=samples, scorer=scorer)
+    assert np.array_equal(a, b)
+
+
+def test_run_is_bit_reproducible(scorer):
+    """Fixed reduction orders everywhere in the fixed point: repeated runs agree bit for bit on
+    everything that does not pass through the B atomics, and to 1e-13 on the global score."""
+    edges, ew, vw, comm, emb = planted_partition(700, 5, 20, seed=705, weighted=True)
+    samples = dv.draw_samples(edges, ew, 700, 1000, 42, False, True)
+    runs = [dv.wGCL(edges, ew, comm, emb, np.zeros(700), vw, *EMPTY, False, 42, 1000, False,
+                    samples=samples, return_stats=True, scorer=scorer) for _ in range(3)]
+    for out, st in runs[1:]:
+        assert list(st.iters) == list(runs[0][1].iters)
+        assert np.array_equal(out[4:], runs[0][0][4:]) and out[0] == runs[0][0][0]
+        np.testing.assert_allclose(out[1], runs[0][0][1], rtol=1e-13)
+    T = scorer.debug_read(1, 700)
+    dv.wGCL(edges, ew, comm, emb, np.zeros(700), vw, *EMPTY, False, 42, 1000, False,
+            samples=samples, scorer=scorer)
+    assert np.array_equal(T, scorer.debug_read(1, 700))

@@ -126,3 +126,14 @@ def test_draw_samples_semantics():
     assert all(dmap[(a, b)] == x for a, b, x in zip(lpi[0], lpj[0], lpw[0]))
     # unseeded: one set per alpha
     assert draw_samples(edges, ew, n, 10, -1, False, True)[0].shape == (40, 10)
+
+
+def test_draw_samples_dense_and_complete_graphs():
+    # complete graph: NE is empty, the reference's sample(NE, ...) throws on an empty collection
+    tri = np.array([[1, 2], [2, 3], [1, 3]])
+    with pytest.raises(ValueError, match="non-empty"):
+        draw_samples(tri, np.ones(3), 3, 5, 42, False, True)
+    # nearly complete graph: the single non-edge is always the one drawn
+    k5 = np.array([[i, j] for i in range(1, 6) for j in range(i + 1, 6) if (i, j) != (2, 4)])
+    _, _, _, ni, nj = draw_samples(k5, np.ones(len(k5)), 5, 20, 42, False, True)
+    assert np.all(ni == 2) and np.all(nj == 4)
