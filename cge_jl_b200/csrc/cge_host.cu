@@ -981,6 +981,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         double mb = 80.0;
         if (const char *e = getenv("CGE_B200_L2_MB")) mb = atof(e);
         A.resident_tiles = (long long)(mb * 1e6 / (TILE_ELEMS * 8.0));
+        if (mb < 0) A.resident_tiles = -1;  // plain evict_normal loads
     }
     A.out_iters = reinterpret_cast<int *>(h->fpres.as<char>());
     A.out_diff = reinterpret_cast<double *>(h->fpres.as<char>() + 8);

@@ -115,6 +115,14 @@ __device__ __forceinline__ uint64_t l2_policy(bool keep) {
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
     return keep ? pl : pf;
 }
+__device__ __forceinline__ uint64_t l2_policy_for(long long local_tile, long long resident_tiles) {
+    if (resident_tiles < 0) {  // leave the decision to the stream's access-policy window
+        uint64_t pn;
+        asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+        return pn;
+    }
+    return l2_policy(local_tile < resident_tiles);
+}
 __device__ __forceinline__ double2 ld_stream(const double2 *p, uint64_t pol) {
     double2 v;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
@@ -421,16 +429,17 @@ __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi
 // ---------------------------------------------------------------------------------------------
 template <int M, bool DIRECTED>
 __global__ void __launch_bounds__(NTHREADS, 2) k_sweep(const __grid_constant__ SweepArgs a) {
-    __shared__ __align__(16) double s_col[2][(DIRECTED ? 2 : 1) * NWARPS * TILE];
+    __shared__ __align__(16) double s_col[2 * 2 * NWARPS * TILE];
     int it = 0;
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++it) {
         const int2 ij = a.tile_ij[t];
         const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
-        const uint64_t pol = l2_policy(t - a.tile_begin < a.resident_tiles);
-        if (DIRECTED)
-            tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[it & 1], pol);
+        const uint64_t pol = l2_policy_for(t - a.tile_begin, a.resident_tiles);
+        double *sc = s_col + (it & 1) * 2 * NWARPS * TILE;
+        if constexpr (DIRECTED)
+            tile_pass_d<M>(qt, ij.x, ij.y, a, sc, pol);
         else
-            tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[it & 1], pol);
+            tile_pass_u<M>(qt, ij.x, ij.y, a, sc, pol);
     }
 }
 
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_bsweep(const __grid_constant__ 
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x) {
         const int2 ij = a.tile_ij[t];
         tile_bpass<M, DIRECTED>(a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS, ij.x, ij.y, a,
-                                l2_policy(t - a.tile_begin < a.resident_tiles));
+                                l2_policy_for(t - a.tile_begin, a.resident_tiles));
     }
 }
 
@@ -484,21 +493,25 @@ template <int M, bool DIRECTED>
 __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_constant__ SweepArgs a) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    __shared__ __align__(16) double s_col[2][(DIRECTED ? 2 : 1) * NWARPS * TILE];
+    __shared__ __align__(16) double s_col[2 * 2 * NWARPS * TILE];
     __shared__ double s_red[(DIRECTED ? 2 : 1) * NWARPS * 32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ngroups = (a.n + 31) / 32;
     double diff = 1.0, eps = a.eps0;
     int it = 0, tile_it = 0;
     while (diff > a.delta && it < a.max_iter) {
+        // tiles are dealt round-robin (t = blockIdx.x + k*gridDim.x): at any moment the grid reads
+        // one contiguous ~38 MB window of the matrix.  Measured alternatives (r01, 10k example):
+        // per-CTA contiguous ranges 86 us/pass, one barrier per two tiles 75 us/pass, this 66.
         for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++tile_it) {
             const int2 ij = a.tile_ij[t];
             const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
-            const uint64_t pol = l2_policy(t - a.tile_begin < a.resident_tiles);
-            if (DIRECTED)
-                tile_pass_d<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1], pol);
+            const uint64_t pol = l2_policy_for(t - a.tile_begin, a.resident_tiles);
+            double *sc = s_col + (tile_it & 1) * 2 * NWARPS * TILE;
+            if constexpr (DIRECTED)
+                tile_pass_d<M>(qt, ij.x, ij.y, a, sc, pol);
             else
-                tile_pass_u<M>(qt, ij.x, ij.y, a, s_col[tile_it & 1], pol);
+                tile_pass_u<M>(qt, ij.x, ij.y, a, sc, pol);
         }
         grid.sync();
         // 32 vertices per CTA step: warp w sums the partial slots b = w, w+8, ..., warp 0 adds
