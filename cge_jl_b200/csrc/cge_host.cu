@@ -725,7 +725,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         if ((rc = b->ensure((size_t)np * 8))) return rc;
     if ((rc = h->B.ensure(std::max<size_t>((size_t)(k * k) * 8, 16)))) return rc;
     if ((rc = h->lohi.ensure(64))) return rc;
-    if ((rc = h->slots.ensure(64))) return rc;
+    if ((rc = h->slots.ensure(128))) return rc;
     if ((rc = h->auc_out.ensure(2 * AUC_MAX_BLOCKS * 8))) return rc;
     if ((rc = h->ensure_pinned(64 + 2 * AUC_MAX_BLOCKS * 8 + (size_t)(k * k) * 8))) return rc;
     if ((rc = h->fpres.ensure(64))) return rc;
@@ -988,14 +988,14 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     A.rank = h->rank;
     A.n_ranks = (driver == CGE_B200_DRIVER_PERSISTENT && h->n_ranks > 1) ? h->n_ranks : 1;
     A.xcap = h->xcap;
-    for (int r = 0; r < 8; ++r) {
-        A.xbuf_peer[r] = reinterpret_cast<double *>(h->xpeer[r]);
-        A.flag_peer[r] = h->xpeer[r] ? reinterpret_cast<unsigned *>(
-                                           static_cast<char *>(h->xpeer[r]) +
-                                           (size_t)2 * h->n_ranks * 2 * (size_t)h->xcap * 8)
-                                     : nullptr;
-    }
+    for (int r = 0; r < 8; ++r) A.xbuf_peer[r] = reinterpret_cast<uint4 *>(h->xpeer[r]);
     A.pass_base = h->pass_total;
+    A.phase_ns = nullptr;
+    const bool phases = getenv("CGE_B200_PHASES") && atoi(getenv("CGE_B200_PHASES"));
+    if (phases) {  // diagnostic: per-phase time of block 0 inside the persistent kernel
+        A.phase_ns = h->slots.as<unsigned long long>() + 8;  // bytes 64..127 of the slots buffer
+        CUDA_TRY(cudaMemsetAsync(A.phase_ns, 0, 64, st));
+    }
     A.emb = h->emb.as<double>();
     A.diag = h->dist.as<double>();
     A.lohi = lohi;
@@ -1225,6 +1225,16 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         std::memcpy(&S.hi, &lh[1], 8);
         std::memcpy(&S.hi_full, &lh[3], 8);
     }
+    if (phases) {
+        unsigned long long ph[8];
+        CUDA_TRY(cudaMemcpy(ph, A.phase_ns, 64, cudaMemcpyDeviceToHost));
+        const double np_ = (double)std::max<int64_t>(S.fp_sweeps, 1) * 1e3;
+        fprintf(stderr,
+                "[cge_b200 rank %d] us per pass (block 0): tiles %.2f | barrier A %.2f | reduce%s %.2f | "
+                "peer wait+sum+update %.2f | barrier C %.2f\n",
+                h->rank, ph[0] / np_, ph[1] / np_, A.n_ranks > 1 ? "+peer stores" : "+update",
+                ph[2] / np_, ph[5] / np_, ph[6] / np_);
+    }
     out[0] = best_alpha; out[1] = best_div; out[2] = best_div_ext; out[3] = best_div_int;
     out[4] = best_alpha_auc; out[5] = best_auc; out[6] = best_auc_err;  // :256
     S.launches = h->launches;
@@ -1362,7 +1372,8 @@ int cge_b200_p2p_export(cge_b200_handle *h, int64_t max_vertices, void *handle_o
     }
     h->p2p_ready = false;
     h->xcap = (max_vertices + TILE - 1) / TILE * TILE;
-    const size_t bytes = (size_t)2 * h->n_ranks * 2 * (size_t)h->xcap * 8 + 256;
+    // [2 parities][n_ranks writers][2][xcap] records of 16 bytes (value halves + pass number)
+    const size_t bytes = (size_t)2 * h->n_ranks * 2 * (size_t)h->xcap * 16;
     CUDA_TRY(cudaMalloc(&h->xbuf, bytes));
     CUDA_TRY(cudaMemset(h->xbuf, 0, bytes));
     CUDA_TRY(cudaDeviceSynchronize());

@@ -59,17 +59,56 @@ struct SweepArgs {
     int rank, n_ranks;     // n_ranks == 1: no exchange
     unsigned pass_base;    // passes completed before this launch (flags only grow)
     long long xcap;        // vertex capacity of one exchange slot
-    double *xbuf_peer[8];  // rank r's exchange buffer [2 parities][n_ranks writers][2][xcap], peer-mapped
-    unsigned *flag_peer[8];  // rank r's arrival flags [n_ranks]
+    uint4 *xbuf_peer[8];   // rank r's exchange buffer [2 parities][n_ranks writers][2][xcap] of 16-byte
+                           // records {lo32, pass_no, hi32, pass_no}, peer-mapped (CUDA IPC)
+    unsigned long long *phase_ns;  // optional [8]: time of block 0 per phase of a pass (CGE_B200_PHASES=1)
 };
 
-__device__ __forceinline__ void st_release_sys_u32(unsigned *p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
-__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// phase clock of block 0 / thread 0: adds the time since the previous mark to phase_ns[slot]
+struct PhaseClock {
+    unsigned long long *acc, last;
+    __device__ __forceinline__ PhaseClock(unsigned long long *p)
+        : acc((blockIdx.x == 0 && threadIdx.x == 0) ? p : nullptr), last(0) {
+        if (acc) last = global_ns();
+    }
+    __device__ __forceinline__ void mark(int slot) {
+        if (acc) {
+            const unsigned long long now = global_ns();
+            acc[slot] += now - last;
+            last = now;
+        }
+    }
+};
+
+// Exchange records carry their own arrival flag (the protocol NCCL calls LL): a double travels
+// as two 8-byte stores {lo32, pass_no} and {hi32, pass_no}; an 8-byte store is atomic, so a
+// reader that sees pass_no in both halves has the value -- no fence, no separate flag, no
+// barrier between the producer's stores and the consumer's loads.
+__device__ __forceinline__ void xchg_store(uint4 *rec, double v, unsigned pass_no) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(rec), "r"((unsigned)b),
+                 "r"(pass_no)
+                 : "memory");
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(
+                     reinterpret_cast<char *>(rec) + 8),
+                 "r"((unsigned)(b >> 32)), "r"(pass_no)
+                 : "memory");
+}
+__device__ __forceinline__ double xchg_load(const uint4 *rec, unsigned pass_no) {
+    unsigned lo, f0, hi, f1, spins = 0;
+    do {
+        asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1)
+                     : "l"(rec)
+                     : "memory");
+        if (++spins > (1u << 26)) __trap();  // a lost peer must not hang the GPU
+    } while (f0 != pass_no || f1 != pass_no);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 
 // Partial slots part[b][v] that this rank's tiles can have written for vertex v (block bv):
@@ -115,8 +154,11 @@ __device__ __forceinline__ uint64_t l2_policy(bool keep) {
     asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
     return keep ? pl : pf;
 }
+// The L2-resident set is the first resident_tiles tiles of the sequence (every CTA starts a pass
+// on L2 hits).  Measured alternative (r01): a staggered set (CTA c keeps its k-th tile when
+// k % P == c % P) is slower for every P tried (P = 4..8: 75..69 us/pass against 67).
 __device__ __forceinline__ uint64_t l2_policy_for(long long local_tile, long long resident_tiles) {
-    if (resident_tiles < 0) {  // leave the decision to the stream's access-policy window
+    if (resident_tiles < 0) {
         uint64_t pn;
         asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
         return pn;
@@ -499,10 +541,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
     const int ngroups = (a.n + 31) / 32;
     double diff = 1.0, eps = a.eps0;
     int it = 0, tile_it = 0;
+    PhaseClock clk(a.phase_ns);
     while (diff > a.delta && it < a.max_iter) {
         // tiles are dealt round-robin (t = blockIdx.x + k*gridDim.x): at any moment the grid reads
         // one contiguous ~38 MB window of the matrix.  Measured alternatives (r01, 10k example):
-        // per-CTA contiguous ranges 86 us/pass, one barrier per two tiles 75 us/pass, this 66.
+        // per-CTA contiguous ranges 86 us/pass, one barrier per two tiles 75, claiming tiles from
+        // a global counter 70, this 66-67.
         for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++tile_it) {
             const int2 ij = a.tile_ij[t];
             const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
@@ -513,24 +557,32 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
             else
                 tile_pass_u<M>(qt, ij.x, ij.y, a, sc, pol);
         }
+        clk.mark(0);  // tiles of block 0
         grid.sync();
+        clk.mark(1);  // waiting for the slowest CTA + barrier
         // 32 vertices per CTA step: warp w sums the partial slots b = w, w+8, ..., warp 0 adds
         // the eight sub-sums in fixed order.  Single GPU: warp 0 applies divergence.jl:160-165 /
         // 451-461 at once.  Multi GPU: the sums of this rank's tiles go to every rank's exchange
-        // buffer over NVLink (plain peer stores), one release flag per peer announces them, and
-        // every rank adds the n_ranks contributions in rank order -- identical T on all ranks,
-        // no host round trip, no separate collective.
+        // buffer over NVLink as self-flagged records (xchg_store), and every rank adds the n_ranks
+        // contributions in rank order as they arrive -- identical T on all ranks, no host round
+        // trip, no separate collective, no extra barrier.
         double e = 0.0;
         const bool multi = a.n_ranks > 1;
         const unsigned pass_no = a.pass_base + (unsigned)it + 1u;
         const size_t xpar = (size_t)(pass_no & 1u) * a.n_ranks;
-        for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        // two 32-vertex groups per CTA step, four warps each (sub-warp q sums slots b = q, q+4, ..):
+        // 592 group slots per round cover the 313 groups of the 10k example in one round
+        constexpr int RW = NWARPS / 2;  // warps per group
+        const int half = w / RW, q4 = w % RW;
+        for (int g0 = blockIdx.x * 2; g0 < ngroups; g0 += gridDim.x * 2) {
+            const int g = g0 + half;
             const int v = g * 32 + lane;
+            const bool live = g < ngroups && v < a.n;
             double pa = 0.0, pb = 0.0;
-            if (v < a.n) {
+            if (live) {
                 int b_lo, b_hi;
                 part_range(a, v, b_lo, b_hi);
-                for (int b = b_lo + w; b < b_hi; b += NWARPS) {
+                for (int b = b_lo + q4; b < b_hi; b += RW) {
                     pa += __ldcg(a.partA + (size_t)b * a.np + v);
                     if (DIRECTED) pb += __ldcg(a.partB + (size_t)b * a.np + v);
                 }
@@ -538,18 +590,18 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
             s_red[w * 32 + lane] = pa;
             if (DIRECTED) s_red[NWARPS * 32 + w * 32 + lane] = pb;
             __syncthreads();
-            if (w == 0 && v < a.n) {
+            if (q4 == 0 && live) {
                 double sa = 0.0, sb = 0.0;
 #pragma unroll
-                for (int w2 = 0; w2 < NWARPS; ++w2) {
-                    sa += s_red[w2 * 32 + lane];
-                    if (DIRECTED) sb += s_red[NWARPS * 32 + w2 * 32 + lane];
+                for (int w2 = 0; w2 < RW; ++w2) {
+                    sa += s_red[(half * RW + w2) * 32 + lane];
+                    if (DIRECTED) sb += s_red[NWARPS * 32 + (half * RW + w2) * 32 + lane];
                 }
                 if (multi) {
                     const size_t o = ((xpar + a.rank) * 2) * (size_t)a.xcap + v;
                     for (int r = 0; r < a.n_ranks; ++r) {
-                        a.xbuf_peer[r][o] = sa;
-                        if (DIRECTED) a.xbuf_peer[r][o + a.xcap] = sb;
+                        xchg_store(a.xbuf_peer[r] + o, sa, pass_no);
+                        if (DIRECTED) xchg_store(a.xbuf_peer[r] + o + a.xcap, sb, pass_no);
                     }
                 } else {
                     e = fmax(e, fp_update<M, DIRECTED>(a, v, sa, sb, eps));
@@ -557,34 +609,25 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
             }
             __syncthreads();
         }
+        clk.mark(2);  // partial-slot reduction (+ update, or peer stores)
         if (multi) {
-            __threadfence_system();
-            grid.sync();  // every peer store of this rank is issued and fenced
-            if (blockIdx.x == 0 && (int)threadIdx.x < a.n_ranks)
-                st_release_sys_u32(a.flag_peer[threadIdx.x] + a.rank, pass_no);
-            if (threadIdx.x == 0) {
-                for (int r = 0; r < a.n_ranks; ++r) {
-                    unsigned spins = 0;
-                    while ((int)(ld_acquire_sys_u32(a.flag_peer[a.rank] + r) - pass_no) < 0)
-                        if (++spins > (1u << 26)) __trap();  // a lost peer must not hang the GPU
-                }
-            }
-            __syncthreads();
-            const double *mine = a.xbuf_peer[a.rank];
+            // every rank adds the n_ranks contributions in rank order as they arrive
+            const uint4 *mine = a.xbuf_peer[a.rank];
             for (int g = blockIdx.x * NWARPS + w; g < ngroups; g += gridDim.x * NWARPS) {
                 const int v = g * 32 + lane;
                 if (v < a.n) {
                     double sa = 0.0, sb = 0.0;
                     for (int r = 0; r < a.n_ranks; ++r) {
                         const size_t o = ((xpar + r) * 2) * (size_t)a.xcap + v;
-                        sa += __ldcg(mine + o);
-                        if (DIRECTED) sb += __ldcg(mine + o + a.xcap);
+                        sa += xchg_load(mine + o, pass_no);
+                        if (DIRECTED) sb += xchg_load(mine + o + a.xcap, pass_no);
                     }
                     e = fmax(e, fp_update<M, DIRECTED>(a, v, sa, sb, eps));
                 }
             }
+            clk.mark(5);  // wait for the peers' sums + update
         }
-        if (w == 0 || multi) {  // max is order independent: one atomic per contributing warp
+        if (w % (NWARPS / 2) == 0 || multi) {  // max is order independent: one atomic per contributing warp
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) e = fmax(e, __shfl_xor_sync(FULL, e, off));
             if (lane == 0 && e > 0.0)
@@ -592,6 +635,7 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
         }
         if (blockIdx.x == 0 && threadIdx.x == 0) a.slots[(it + 1) % 3] = 0ull;
         grid.sync();
+        clk.mark(6);  // residual barrier
         const double f = __longlong_as_double((long long)__ldcg(a.slots + it % 3));
         if (DIRECTED && f > diff) eps *= 0.99;  // divergence.jl:462-464
         diff = f;

@@ -158,8 +158,8 @@ int cge_b200_comm_init(cge_b200_handle *h, const void *id_bytes, int rank, int n
 
 /* Optional NVLink peer-memory exchange for the multi-GPU persistent driver: instead of one NCCL
  * all-reduce per pass issued by the host, the fixed-point kernel itself stores its partial degree
- * sums into every peer's exchange buffer and synchronises with release/acquire flags, so a whole
- * alpha runs in one launch on every rank.  After comm_init: every rank calls p2p_export (allocates
+ * sums into every peer's exchange buffer as self-flagged 8-byte records (value half + pass
+ * number) that the peers poll, so a whole alpha runs in one launch on every rank.  After comm_init: every rank calls p2p_export (allocates
  * its buffer for up to max_vertices vertices, returns a 64-byte CUDA IPC handle), the caller
  * all-gathers the handles, every rank calls p2p_import with the n_ranks x 64 bytes.  Without it
  * multi-rank runs fall back to the NCCL host loop. */
