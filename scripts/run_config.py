@@ -50,6 +50,12 @@ def build(cfg):
     elif cfg == 4:
         edges, ew, vw, comm, emb = planted_partition(200000, k=64, d=128, seed=1004)
         name = "synthetic 200k-node planted-partition graph, 64 communities, d=128, exact"
+    elif isinstance(cfg, str):  # "n,d,k,directed" -- ad-hoc synthetic problem (profiling)
+        n, d, k, dr = (int(x) for x in cfg.split(","))
+        directed = bool(dr)
+        edges, ew, vw, comm, emb = planted_partition(n, k=k, d=d, seed=7, directed=directed,
+                                                     weighted=directed)
+        name = f"synthetic planted partition n={n} d={d} k={k} directed={directed}"
     else:
         raise SystemExit("config 5 (1M vertices) needs the recompute regime at scale: not run in round 1")
     return dict(edges=edges, ew=ew, vw=vw, comm=comm, emb=emb, directed=directed, lm=lm, name=name,
@@ -58,7 +64,8 @@ def build(cfg):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, required=True)
+    ap.add_argument("--config", type=int, default=0)
+    ap.add_argument("--synthetic", default="", help="n,d,k,directed instead of --config")
     ap.add_argument("--samples", type=int, default=10000)
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--regime", type=int, default=0)
@@ -73,7 +80,7 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    c = build(args.config)
+    c = build(args.synthetic or args.config)
     n = c["vw"].shape[0]
     t0 = time.perf_counter()
     if c["lm"] is None:
