@@ -869,10 +869,9 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     S.n_tiles = (int)h->n_tiles;
     S.grid = grid;
     S.matrix_bytes = stored ? (int64_t)local_tiles * TILE_ELEMS * 8 : 0;
-    cudaEvent_t ev0, ev1, ev2;
-    CUDA_TRY(cudaEventCreate(&ev0));
-    CUDA_TRY(cudaEventCreate(&ev1));
-    CUDA_TRY(cudaEventCreate(&ev2));
+    // three phase markers come from the handle's event pool (no create/destroy per run, nothing
+    // to leak on the error paths below)
+    cudaEvent_t ev0 = h->next_event(), ev1 = h->next_event(), ev2 = h->next_event();
     CUDA_TRY(cudaEventRecord(ev0, st));
 
     // ---- distances, extrema, q (divergence.jl:79-93 / 359-375) ----
@@ -1210,12 +1209,9 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventElapsedTime(&S.ms_build, ev0, ev1));
     CUDA_TRY(cudaEventElapsedTime(&S.ms_solve, ev1, ev2));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
-    cudaEventDestroy(ev2);
     for (size_t i = 0; i < h->ev_is_b.size(); ++i) {
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, h->evpool[2 * i], h->evpool[2 * i + 1]) == cudaSuccess)
+        float ms = 0.f;  // pool entries 0..2 are the phase markers, sweep pairs follow
+        if (cudaEventElapsedTime(&ms, h->evpool[3 + 2 * i], h->evpool[4 + 2 * i]) == cudaSuccess)
             (h->ev_is_b[i] ? S.ms_bsweeps : S.ms_sweeps) += ms;
     }
     {

@@ -32,7 +32,13 @@ EMPTY = (np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int
 def build(cfg):
     t0 = time.perf_counter()
     directed, lm = False, None
-    if cfg in (1, 2):
+    if isinstance(cfg, str):  # "n,d,k,directed" -- ad-hoc synthetic problem (profiling)
+        n, d, k, dr = (int(x) for x in cfg.split(","))
+        directed = bool(dr)
+        edges, ew, vw, comm, emb = planted_partition(n, k=k, d=d, seed=7, directed=directed,
+                                                     weighted=directed)
+        name = f"synthetic planted partition n={n} d={d} k={k} directed={directed}"
+    elif cfg in (1, 2):
         z = np.load(os.path.join(ROOT, "tests", "golden", "example10k.npz"))
         edges, ew, vw, comm, emb = (z[k] for k in ("edges", "eweights", "vweights", "comm", "embedding"))
         name = "10k example, -l 200 --seed 42 (landmarks)" if cfg == 1 else "10k example --force-exact"
@@ -50,14 +56,20 @@ def build(cfg):
     elif cfg == 4:
         edges, ew, vw, comm, emb = planted_partition(200000, k=64, d=128, seed=1004)
         name = "synthetic 200k-node planted-partition graph, 64 communities, d=128, exact"
-    elif isinstance(cfg, str):  # "n,d,k,directed" -- ad-hoc synthetic problem (profiling)
-        n, d, k, dr = (int(x) for x in cfg.split(","))
-        directed = bool(dr)
-        edges, ew, vw, comm, emb = planted_partition(n, k=k, d=d, seed=7, directed=directed,
-                                                     weighted=directed)
-        name = f"synthetic planted partition n={n} d={d} k={k} directed={directed}"
+    elif cfg == 5:
+        # the landmark half of BASELINE.json configs[4]: 1M vertices, d = 128, rss landmarks -l 4000
+        # on one GPU (the exact half needs 4 TB of pairs: recompute regime at scale, not in round 1)
+        edges, ew, vw, comm, emb = planted_partition(1000000, k=64, d=128, seed=1005)
+        name = "synthetic 1M-node planted-partition graph, d=128, k=64, rss landmarks -l 4000 (1 GPU)"
+        by = {}
+        for v, c in enumerate(comm[:, 0], start=1):
+            by.setdefault(int(c), []).append(v)
+        t1 = time.perf_counter()
+        lm = landmarks(edges, ew, vw, [np.asarray(v) for v in by.values()], comm, emb, False,
+                       4000, 4, split_cluster_rss, False)
+        print(f"landmarks(): {time.perf_counter() - t1:.1f} s, N = {lm[1].shape[0]}", flush=True)
     else:
-        raise SystemExit("config 5 (1M vertices) needs the recompute regime at scale: not run in round 1")
+        raise SystemExit("unknown config")
     return dict(edges=edges, ew=ew, vw=vw, comm=comm, emb=emb, directed=directed, lm=lm, name=name,
                 t_gen=time.perf_counter() - t0)
 
