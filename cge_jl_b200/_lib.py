@@ -63,6 +63,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "cge_b200_version", "cge_b200_device_count", "cge_b200_last_error", "cge_b200_score",
+    "cge_b200_score_multi",
     "cge_b200_create", "cge_b200_destroy", "cge_b200_upload", "cge_b200_run",
     "cge_b200_comm_id_size", "cge_b200_comm_unique_id", "cge_b200_comm_init",
     "cge_b200_shard_plan", "cge_b200_debug_read", "cge_b200_p2p_handle_size",
@@ -88,6 +89,8 @@ def load():
     lib.cge_b200_device_count.restype = C.c_int
     lib.cge_b200_last_error.restype = C.c_char_p
     lib.cge_b200_score.argtypes = [C.POINTER(Problem), _pd, C.POINTER(C.c_int32), C.POINTER(Stats)]
+    lib.cge_b200_score_multi.argtypes = [C.POINTER(Problem), C.c_int, _pd, C.POINTER(C.c_int32),
+                                         C.POINTER(Stats)]
     lib.cge_b200_create.argtypes = [C.c_int, C.POINTER(vp)]
     lib.cge_b200_destroy.argtypes = [vp]
     lib.cge_b200_destroy.restype = None

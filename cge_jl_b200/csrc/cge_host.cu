@@ -13,7 +13,11 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -469,6 +473,39 @@ static double js_bins(const std::vector<double> &C, const std::vector<double> &B
 
 using namespace cge;
 
+// Ranks that live in ONE process (cge_b200_score_multi: one host thread per GPU).  They exchange
+// the per-pass sums exactly like separate processes do (peer stores inside the kernel) but reach
+// the peers' buffers through plain peer access, and the two tiny host-visible reductions (distance
+// extrema, B matrix) go through this structure instead of NCCL.
+struct LocalGroup {
+    int n = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned long gen = 0;
+    std::atomic<int> failed{0};
+    std::vector<unsigned long long> lohi;  // [n][2]
+    std::vector<double> B;                 // [n][k*k]
+    // returns false when some rank has failed (everybody then gives up instead of waiting)
+    bool barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const unsigned long g = gen;
+        if (++arrived == n) {
+            arrived = 0;
+            ++gen;
+            cv.notify_all();
+        } else {
+            cv.wait(lk, [&] { return gen != g || failed.load() != 0; });
+        }
+        return failed.load() == 0;
+    }
+    void fail() {
+        failed.store(1);
+        std::lock_guard<std::mutex> lk(mu);
+        cv.notify_all();
+    }
+};
+
 struct cge_b200_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -490,6 +527,7 @@ struct cge_b200_handle {
     int64_t xcap = 0;               // vertex capacity of a slot
     bool p2p_ready = false;
     unsigned pass_total = 0;        // fixed-point passes executed with the exchange so far
+    LocalGroup *group = nullptr;    // set when the ranks are threads of this process
     // host copies
     std::vector<int64_t> perm;           // sorted position -> caller's 0-based vertex
     std::vector<double> C;               // k*k observed community mass (divergence.jl:55-63/337-345)
@@ -839,6 +877,9 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     // the persistent kernel cannot call NCCL between passes: multi-rank runs use the host loop
     const bool can_p2p = h->n_ranks > 1 && h->p2p_ready && h->np <= h->xcap &&
                          h->regime == CGE_B200_REGIME_STORED;
+    if (h->group && !can_p2p)
+        return fail(CGE_B200_ERR_STATE,
+                    "in-process multi-GPU needs the stored regime and the peer exchange");
     const int driver =
         h->n_ranks > 1 ? ((can_p2p && h->driver != CGE_B200_DRIVER_HOSTLOOP)
                               ? CGE_B200_DRIVER_PERSISTENT
@@ -898,7 +939,22 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                                                            lohi);
         ++h->launches;
     }
-    if (h->n_ranks > 1) {
+    if (h->n_ranks > 1 && h->group) {
+        LocalGroup &G = *h->group;
+        unsigned long long mine[2];
+        CUDA_TRY(cudaMemcpyAsync(mine, lohi, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        G.lohi[2 * h->rank] = mine[0];
+        G.lohi[2 * h->rank + 1] = mine[1];
+        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        for (int r = 0; r < G.n; ++r) {  // bit patterns of non-negative doubles order like the values
+            mine[0] = std::min(mine[0], G.lohi[2 * r]);
+            mine[1] = std::max(mine[1], G.lohi[2 * r + 1]);
+        }
+        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        CUDA_TRY(cudaMemcpyAsync(lohi, mine, 16, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // `mine` is a local
+    } else if (h->n_ranks > 1) {
         if (int rc = nccl_check(g_nccl.AllReduce(lohi, lohi, 1, kNcclU64, kNcclMin, h->nccl_comm, st),
                                 "ncclAllReduce(min)"))
             return rc;
@@ -1144,7 +1200,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 ++h->launches;
             }
             ++S.b_sweeps;
-            if (h->n_ranks > 1)
+            if (h->n_ranks > 1 && !h->group)
                 if (int rc = nccl_check(g_nccl.AllReduce(h->B.p, h->B.p, (size_t)k * k, kNcclF64,
                                                          kNcclSum, h->nccl_comm, st),
                                         "ncclAllReduce(B)"))
@@ -1152,6 +1208,18 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             CUDA_TRY(cudaMemcpyAsync(pin_B, h->B.p, (size_t)k * k * 8, cudaMemcpyDeviceToHost, st));
         }
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (do_div && h->n_ranks > 1 && h->group) {  // sum the ranks' B on the host, in rank order
+            LocalGroup &G = *h->group;
+            const size_t kk = (size_t)k * k;
+            std::memcpy(G.B.data() + (size_t)h->rank * kk, pin_B, kk * 8);
+            if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+            for (size_t i = 0; i < kk; ++i) {
+                double acc = 0.0;
+                for (int r = 0; r < G.n; ++r) acc += G.B[(size_t)r * kk + i];
+                pin_B[i] = acc;
+            }
+            if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        }
         if (driver != CGE_B200_DRIVER_HOSTLOOP) {
             std::memcpy(&it, pin, 4);
             std::memcpy(&diff, pin + 8, 8);
@@ -1314,9 +1382,99 @@ int cge_b200_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_sta
     return do_run(h, out, out_len, stats);
 }
 
+int cge_b200_score_multi(const cge_b200_problem *p, int n_gpus, double *out, int32_t *out_len,
+                         cge_b200_stats *stats) {
+    if (!p || !out || !out_len) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    if (n_gpus < 2 || n_gpus > 8) return fail(CGE_B200_ERR_ARG, "n_gpus must be 2..8");
+    if (cge_b200_device_count() < n_gpus) return fail(CGE_B200_ERR_CUDA, "not enough CUDA devices");
+    if (p->n_full > 0)
+        return fail(CGE_B200_ERR_ARG, "landmark-mode runs stay on one GPU (replicas only)");
+    LocalGroup G;
+    G.n = n_gpus;
+    G.lohi.assign((size_t)2 * n_gpus, 0ull);
+    std::vector<cge_b200_handle *> hs((size_t)n_gpus, nullptr);
+    std::vector<int> rcs((size_t)n_gpus, 0);
+    std::vector<std::string> errs((size_t)n_gpus);
+    std::vector<double> outs((size_t)n_gpus * 7, 0.0);
+    std::vector<int32_t> lens((size_t)n_gpus, 7);
+    std::vector<cge_b200_stats> sts((size_t)n_gpus);
+    // n = maximum(edges) decides the exchange capacity and the size of the B scratch
+    int64_t n = 0, k = 0;
+    for (int64_t e = 0; e < p->m; ++e)
+        n = std::max(n, std::max(p->edge_src[e], p->edge_dst[e]) - p->index_base + 1);
+    for (int64_t i = 0; i < std::min(n, p->n_comm); ++i) k = std::max(k, p->comm[i] - p->index_base + 1);
+    if (n <= 0 || k <= 0) return fail(CGE_B200_ERR_ARG, "empty problem");
+    G.B.assign((size_t)n_gpus * (size_t)(k * k), 0.0);
+    auto worker = [&](int r) {
+        auto bail = [&](int rc) {
+            rcs[(size_t)r] = rc;
+            errs[(size_t)r] = g_err;
+            G.fail();
+        };
+        int rc = cge_b200_create(r, &hs[(size_t)r]);
+        if (rc) return bail(rc);
+        cge_b200_handle *h = hs[(size_t)r];
+        h->rank = r;
+        h->n_ranks = n_gpus;
+        h->group = &G;
+        // exchange buffer: same layout as cge_b200_p2p_export, reached by plain peer access
+        h->xcap = (n + TILE - 1) / TILE * TILE;
+        const size_t bytes = (size_t)2 * n_gpus * 2 * (size_t)h->xcap * 16;
+        if (cudaMalloc(&h->xbuf, bytes) != cudaSuccess || cudaMemset(h->xbuf, 0, bytes) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) {
+            cudaGetLastError();
+            fail(CGE_B200_ERR_OOM, "exchange buffer allocation failed");
+            return bail(CGE_B200_ERR_OOM);
+        }
+        for (int q = 0; q < n_gpus; ++q)
+            if (q != r) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(q, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                    fail(CGE_B200_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                    return bail(CGE_B200_ERR_CUDA);
+                }
+                cudaGetLastError();
+            }
+        if (!G.barrier()) return;
+        for (int q = 0; q < n_gpus; ++q) h->xpeer[q] = hs[(size_t)q]->xbuf;
+        h->p2p_ready = true;
+        rc = cge_b200_upload(h, p);
+        if (rc) return bail(rc);
+        if (!G.barrier()) return;  // nobody launches a kernel that waits for a rank that gave up
+        rc = cge_b200_run(h, &outs[(size_t)r * 7], &lens[(size_t)r], &sts[(size_t)r]);
+        if (rc) return bail(rc);
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_gpus; ++r) th.emplace_back(worker, r);
+    for (auto &t : th) t.join();
+    int rc = 0;
+    for (int r = 0; r < n_gpus && !rc; ++r)
+        if (rcs[(size_t)r]) {
+            rc = rcs[(size_t)r];
+            g_err = "rank " + std::to_string(r) + ": " + errs[(size_t)r];
+        }
+    if (!rc && G.failed.load()) rc = fail(CGE_B200_ERR_STATE, "a rank failed");
+    for (int r = 0; r < n_gpus; ++r)
+        if (hs[(size_t)r]) {
+            for (int q = 0; q < 8; ++q) hs[(size_t)r]->xpeer[q] = nullptr;  // not IPC mappings
+            cge_b200_destroy(hs[(size_t)r]);
+        }
+    if (rc) return rc;
+    std::memcpy(out, outs.data(), 7 * sizeof(double));
+    *out_len = lens[0];
+    if (stats) *stats = sts[0];
+    return 0;
+}
+
 int cge_b200_score(const cge_b200_problem *p, double *out, int32_t *out_len,
                    cge_b200_stats *stats) {
     if (!p || !out || !out_len) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    // CGE_B200_GPUS=N shards an exact-mode call over N GPUs of this box without any change to
+    // the caller (the Julia wrapper keeps calling cge_b200_score)
+    if (const char *e = getenv("CGE_B200_GPUS")) {
+        const int g = atoi(e);
+        if (g > 1 && p->n_full == 0) return cge_b200_score_multi(p, g, out, out_len, stats);
+    }
     cge_b200_handle *h = nullptr;
     int rc = cge_b200_create(0, &h);
     if (rc) return rc;

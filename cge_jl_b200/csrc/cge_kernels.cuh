@@ -267,7 +267,9 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
 //   Sout_i += Tin_j * Tout_i * g     Sout_j += Tin_i * Tout_j * g
 // partA collects the Sin sums without their own Tin factor, partB the Sout sums without Tout.
 // The second copy of the diagonal term (i == j is added twice at :444-447) is added by the
-// finalize kernel.
+// finalize kernel.  Two batches of 8 rows at two CTAs per SM: a single 16-row loop with 32 row
+// accumulators needs 255 registers (one CTA per SM) and measured slower (config 3: 2.32 ms per
+// pass against 2.00).
 // ---------------------------------------------------------------------------------------------
 template <int M>
 __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int bi, int bj,

@@ -176,6 +176,19 @@ class Scorer:
         return buf.reshape(n, n) if what == 0 else buf
 
 
+def score_multi(problem, n_gpus):
+    """``cge_b200_score_multi``: one call, ``n_gpus`` GPUs of this box driven by threads of this
+    process (what a single-process host such as Julia uses; ``CGE_B200_GPUS`` does the same for
+    plain ``cge_b200_score``).  Returns ``(out, stats)``."""
+    lib = _lib.load()
+    out = np.zeros(7)
+    n_out = C.c_int32(7)
+    stats = _lib.Stats()
+    _check(lib.cge_b200_score_multi(C.byref(problem), int(n_gpus), _pd(out), C.byref(n_out),
+                                    C.byref(stats)))
+    return out[: n_out.value].copy(), stats
+
+
 def unique_id():
     lib = _lib.load()
     buf = C.create_string_buffer(lib.cge_b200_comm_id_size())

@@ -141,6 +141,13 @@ const char *cge_b200_last_error(void);       /* thread-local message of the last
 int cge_b200_score(const cge_b200_problem *p, double *out, int32_t *out_len,
                    cge_b200_stats *stats);
 
+/* The same call sharded over n_gpus (2..8) GPUs of this box from ONE process: one host thread per
+ * GPU, tiles split by cge_b200_shard_plan, per-pass exchange over NVLink peer memory inside the
+ * kernel.  Exact mode only (landmark-mode problems stay on one GPU).  cge_b200_score itself does
+ * this when the environment variable CGE_B200_GPUS=N is set, so hosts need no code change. */
+int cge_b200_score_multi(const cge_b200_problem *p, int n_gpus, double *out, int32_t *out_len,
+                         cge_b200_stats *stats);
+
 /* Handle API: keeps device buffers between calls and separates the host->device stage from
  * the device-resident run (bench.py times them separately). */
 int cge_b200_create(int device, cge_b200_handle **out);

@@ -8,6 +8,9 @@
 # reference does (divergence.jl:121-137, 184-210, 484-513), so with the same seed the GPU sees the
 # very sample sets the Julia implementation would have used.
 #
+# Multi-GPU: set ENV["CGE_B200_GPUS"] = "8" before calling wGCL in exact mode; the library then
+# shards the pair matrix over the GPUs of the box from this single process (cge_b200_score_multi).
+#
 # NOTE: Julia is not installed in the image this repository is built and tested in; this file is
 # the binding a maintainer adds on the reference side (INTEGRATION.md) and mirrors, line for line,
 # cge_jl_b200/divergence.py, which IS exercised by the test-suite through the same C ABI.

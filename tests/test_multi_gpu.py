@@ -93,3 +93,28 @@ def test_two_gpu_matches_one_gpu_and_oracle(directed, p2p):
         n_alpha_run = tr.n_alpha_run
         iters, div, auc = iters2, div2, auc2
     assert_parity(out2, St, ref, tr)
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_single_process_two_gpus(directed):
+    """cge_b200_score_multi: the ranks are threads of one process (the Julia ccall case); peers
+    are reached by plain peer access, extrema and B are reduced on the host."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cge_jl_b200 import divergence as dv
+    from util import RTOL, empty_landmark_args
+
+    n, edges, ew, vw, comm, emb = _problem(directed)
+    samples = dv.draw_samples(edges, ew, n, 2000, 42, directed, True)
+    p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False,
+                              directed, samples)
+    out2, st2 = dv.score_multi(p, 2)
+    assert st2.n_ranks == 2 and st2.driver == 2
+    f = dv.wGCL_directed if directed else dv.wGCL
+    out1, st1 = f(edges, ew, comm, emb, np.zeros(n), vw, *empty_landmark_args(), False, 42, 2000,
+                  False, samples=samples, return_stats=True)
+    assert list(st1.iters) == list(st2.iters)
+    assert out1[0] == out2[0] and out1[4] == out2[4]
+    np.testing.assert_allclose(out2, out1, rtol=RTOL, atol=1e-15)
+    del keep
