@@ -890,6 +890,10 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     S.driver = driver;
     S.regime = h->regime;
     const bool stored = h->regime == CGE_B200_REGIME_STORED;
+    // small problems (fewer tiles than resident CTAs): one run-time-exponent kernel for the whole
+    // alpha grid instead of one instantiation per alpha (first-use load time, see powm_any)
+    bool small = stored && (h->tile_end - h->tile_begin) < 2 * (int64_t)h->sm_count;
+    if (const char *e = getenv("CGE_B200_RT_EXPONENT")) small = stored && atoi(e) != 0;
     S.ms_upload = h->ms_upload;
     if (h->star) {  // divergence.jl:332-334
         out[0] = -1.0;
@@ -1093,6 +1097,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             const bool ring = stored && driver == CGE_B200_DRIVER_RING;
             const void *fn = !stored ? fp_kernel_rc(h->directed)
                              : ring  ? fp_ring_kernel(m, h->directed)
+                             : small ? fp_kernel_rt(h->directed)
                                      : fp_kernel(m, h->directed);
             const int threads = ring ? fp_ring_threads() : NTHREADS;
             const size_t smem = ring ? fp_ring_smem_bytes(h->directed) : 0;
@@ -1120,8 +1125,9 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         while (driver == CGE_B200_DRIVER_HOSTLOOP && diff > delta) {  // :151 / :436
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
-                if (stored) launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
-                else launch_tiles_rc(h->directed ? 1 : 0, grid, st, A);
+                if (!stored) launch_tiles_rc(h->directed ? 1 : 0, grid, st, A);
+                else if (small) launch_tiles_rt(h->directed ? 1 : 0, grid, st, A);
+                else launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
                 cudaEventRecord(h->next_event(), st);
                 h->ev_is_b.push_back(0);
                 ++h->launches;
@@ -1193,8 +1199,9 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
-                if (stored) launch_tiles(m, h->directed ? 3 : 2, grid, st, A);
-                else launch_tiles_rc(h->directed ? 3 : 2, grid, st, A);
+                if (!stored) launch_tiles_rc(h->directed ? 3 : 2, grid, st, A);
+                else if (small) launch_tiles_rt(h->directed ? 3 : 2, grid, st, A);
+                else launch_tiles(m, h->directed ? 3 : 2, grid, st, A);
                 cudaEventRecord(h->next_event(), st);
                 h->ev_is_b.push_back(1);
                 ++h->launches;

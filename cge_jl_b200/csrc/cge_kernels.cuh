@@ -143,6 +143,18 @@ __device__ __forceinline__ double powm_rt(double q, int m) {
     }
     return r;
 }
+// M > 0: compile-time exponent (the large-problem kernels, one instantiation per alpha);
+// M == 0: exponent read from the arguments -- ONE kernel for the whole alpha grid.  Small problems
+// (landmark mode: a few hundred to a few thousand vertices) are latency bound, and for them the
+// ~10 ms CUDA needs to load each of 80 kernel instantiations on first use would dwarf the run.
+template <int M>
+__device__ __forceinline__ double powm_any(double q, int m_rt) {
+    if constexpr (M == 0) {
+        return powm_rt(q, m_rt);
+    } else {
+        return powm<M>(q);
+    }
+}
 
 // 16-byte load of matrix data: read once per pass, kept out of L1.  The L2 policy decides what
 // survives from one pass to the next: the first `resident_tiles` tiles are loaded evict_last (they
@@ -235,8 +247,8 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
         const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
         const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
         const double ti = __shfl_sync(FULL, trow, rr);
-        const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
-        const double g2 = powm<M>(v23.x), g3 = powm<M>(v23.y);
+        const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
+        const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
         racc[rr] = fma(g3, tc23.y, fma(g2, tc23.x, fma(g1, tc01.y, g0 * tc01.x)));
         c0 = fma(ti, g0, c0);
         c1 = fma(ti, g1, c1);
@@ -297,8 +309,8 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
             const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
             const double t_in = __shfl_sync(FULL, trow_in, rr);
             const double t_out = __shfl_sync(FULL, trow_out, rr);
-            const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
-            const double g2 = powm<M>(v23.x), g3 = powm<M>(v23.y);
+            const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
+            const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
             rin[r8] = fma(g3, to23.y, fma(g2, to23.x, fma(g1, to01.y, g0 * to01.x)));
             rout[r8] = fma(g3, ti23.y, fma(g2, ti23.x, fma(g1, ti01.y, g0 * ti01.x)));
             ci0 = fma(t_out, g0, ci0);
@@ -448,8 +460,8 @@ __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi
                     cur = cr;
                 }
             }
-            double g[4] = {powm<M>(v01[cb][r8].x), powm<M>(v01[cb][r8].y),
-                           powm<M>(v23[cb][r8].x), powm<M>(v23[cb][r8].y)};
+            double g[4] = {powm_any<M>(v01[cb][r8].x, a.m), powm_any<M>(v01[cb][r8].y, a.m),
+                           powm_any<M>(v23[cb][r8].x, a.m), powm_any<M>(v23[cb][r8].y, a.m)};
             if (!DIRECTED && diag) {  // unordered pairs once: keep col >= row (divergence.jl:229-230)
                 const int gr = bi * TILE + row0 + rr;
 #pragma unroll
@@ -510,7 +522,7 @@ __device__ __forceinline__ double fp_update(const SweepArgs &a, int v, double sa
         e = fabs(wv - s);
     } else {
         const double ti = __ldcg(a.Ta + v), to = __ldcg(a.Tb + v);
-        const double gd = powm<M>(a.qdiag[v]);
+        const double gd = powm_any<M>(a.qdiag[v], a.m);
         const double sin = ti * (sa + to * gd), sout = to * (sb + ti * gd);
         a.S_a[v] = sin;
         a.S_b[v] = sout;
@@ -673,6 +685,9 @@ const void *fp_ring_kernel_part5(int m, int directed);
 const void *fp_ring_kernel_part6(int m, int directed);
 const void *fp_ring_kernel_part7(int m, int directed);
 size_t fp_ring_smem_bytes(int directed);
+// stored regime with a run-time exponent (small problems): kind as in launch_tiles
+void launch_tiles_rt(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
+const void *fp_kernel_rt(int directed);
 // recompute regime (cge_recompute.cu): kind as in launch_tiles, exponent taken from a.m
 void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 const void *fp_kernel_rc(int directed);

@@ -142,8 +142,8 @@ __device__ __forceinline__ void ring_tile(int bi, int bj, const SweepArgs &a, do
             const int idx = qtr * 4 + r;
             const double2 v01 = *reinterpret_cast<const double2 *>(sp + r * TILE + 2 * lane);
             const double2 v23 = *reinterpret_cast<const double2 *>(sp + r * TILE + 64 + 2 * lane);
-            const double g0 = powm<M>(v01.x), g1 = powm<M>(v01.y);
-            const double g2 = powm<M>(v23.x), g3 = powm<M>(v23.y);
+            const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
+            const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
             if (!DIRECTED) {
                 const double ti = __shfl_sync(FULL, trow_a, idx);
                 ra[idx] = fma(g3, ta23.y, fma(g2, ta23.x, fma(g1, ta01.y, g0 * ta01.x)));
@@ -299,7 +299,7 @@ k_fixed_point_ring(const __grid_constant__ SweepArgs a) {
                     e = fmax(e, fabs(wv - s));
                 } else {
                     const double ti = __ldcg(a.Ta + v), to = __ldcg(a.Tb + v);
-                    const double gd = powm<M>(a.qdiag[v]);
+                    const double gd = powm_any<M>(a.qdiag[v], a.m);
                     const double sin = ti * (sa + to * gd), sout = to * (sb + ti * gd);
                     a.S_a[v] = sin;
                     a.S_b[v] = sout;
