@@ -585,6 +585,13 @@ static std::vector<int2> make_tile_table(int64_t nb) {
 
 static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     auto t0 = std::chrono::steady_clock::now();
+    const bool trace = getenv("CGE_B200_PHASES") && atoi(getenv("CGE_B200_PHASES"));
+    auto lap = [&](const char *what) {
+        if (trace)
+            fprintf(stderr, "[cge_b200 upload] %-28s %.3f ms\n", what,
+                    std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0)
+                        .count());
+    };
     if (!p || p->struct_size != (int32_t)sizeof(cge_b200_problem))
         return fail(CGE_B200_ERR_ARG, "cge_b200_problem.struct_size mismatch");
     if (p->index_base != 0 && p->index_base != 1) return fail(CGE_B200_ERR_ARG, "index_base");
@@ -693,6 +700,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     const int64_t np = h->np, dp = h->dp;
+    lap("validate, sort, C, degrees");
     // sorted + padded per-vertex arrays
     std::vector<double> emb((size_t)(np * dp), 0.0), dist((size_t)np, 0.0), w((size_t)np, 1.0),
         w2, Ta((size_t)np, 0.0), Tb;
@@ -731,6 +739,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         if ((rc = upload_vec(h->w2, w2.data(), w2.size() * 8, st))) return rc;
         if ((rc = upload_vec(h->T0b, Tb.data(), Tb.size() * 8, st))) return rc;
     }
+    lap("per-vertex arrays uploaded");
     // tile table and this rank's share
     h->n_tiles = h->nb * (h->nb + 1) / 2;
     shard_range(h->n_tiles, h->rank, h->n_ranks, &h->tile_begin, &h->tile_end);
@@ -742,8 +751,11 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     const size_t local_tiles = (size_t)(h->tile_end - h->tile_begin);
     const size_t q_bytes = std::max<size_t>(local_tiles, 1) * TILE_ELEMS * 8;
     h->regime = p->regime;
-    if (h->regime == CGE_B200_REGIME_AUTO) {
+    if (h->regime == CGE_B200_REGIME_AUTO && h->q.cap >= q_bytes) {
+        h->regime = CGE_B200_REGIME_STORED;  // the handle already holds a large enough matrix
+    } else if (h->regime == CGE_B200_REGIME_AUTO) {
         // stored when the tiles fit next to everything else (2 GB + 5 % head-room), else recompute
+        // (cudaMemGetInfo costs milliseconds: only asked when the matrix has to be (re)allocated)
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
         const size_t avail = free_b + h->q.cap;
@@ -768,6 +780,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     if ((rc = h->ensure_pinned(64 + 2 * AUC_MAX_BLOCKS * 8 + (size_t)(k * k) * 8))) return rc;
     if ((rc = h->fpres.ensure(64))) return rc;
 
+    lap("tile table, buffers");
     // landmark mode: original graph arrays for the local score
     if (h->landmark && h->K > 0) {
         if (!p->init_vweights || !p->v_to_l || !p->init_embed)
@@ -851,6 +864,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     h->uploaded = true;
+    lap("samples");
     h->ms_upload =
         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return 0;

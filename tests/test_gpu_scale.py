@@ -1,0 +1,82 @@
+"""GPU: sizes the oracle cannot reach in seconds -- parity through size-independent properties
+(SURVEY.md section 7): the fixed point converged for the last alpha (max |w - S| <= 0.001 on the
+probe of the final S), all drivers and both regimes agree with each other, pads and ragged last
+tiles do not leak (n deliberately not a multiple of 128)."""
+import numpy as np
+import pytest
+
+from cge_jl_b200 import divergence as dv
+from cge_jl_b200.synth import planted_partition
+from util import empty_landmark_args
+
+pytestmark = pytest.mark.gpu
+EMPTY = empty_landmark_args()
+
+
+def _run(scorer, directed, data, samples, driver, regime, n):
+    edges, ew, vw, comm, emb = data
+    f = dv.wGCL_directed if directed else dv.wGCL
+    out, st = f(edges, ew, comm, emb, np.zeros(n), vw, *EMPTY, False, 42, samples[0].shape[1],
+                False, samples=samples, return_stats=True, scorer=scorer, driver=driver,
+                regime=regime)
+    return out, st
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_20k_properties_and_driver_agreement(scorer, directed):
+    n = 20011
+    data = planted_partition(n, k=24, d=48, seed=31, directed=directed, weighted=directed)
+    edges, ew, vw = data[0], data[1], data[2]
+    samples = dv.draw_samples(edges, ew, n, 5000, 42, directed, True)
+    out, st = _run(scorer, directed, data, samples, 2, 1, n)
+    assert np.all(np.isfinite(out)) and out[0] * 4 == round(out[0] * 4)
+    assert st.n_alpha_run >= 6 and min(list(st.iters)[: st.n_alpha_run]) >= 1
+    # converged degrees on the final probe
+    if directed:
+        din, dout = np.zeros(n), np.zeros(n)
+        np.add.at(dout, edges[:, 0] - 1, ew)
+        np.add.at(din, edges[:, 1] - 1, ew)
+        sin, sout = scorer.debug_read(3, n), scorer.debug_read(4, n)
+        assert np.abs(din - sin)[din > 0].max() <= 0.001
+        assert np.abs(dout - sout)[dout > 0].max() <= 0.001
+    else:
+        assert np.abs(vw - scorer.debug_read(3, n)).max() <= 0.001
+    assert np.isclose(out[6], 1.96 * np.sqrt(out[5] * (1 - out[5]) / 5000))
+    # the host-loop driver walks through the same passes and lands on the same numbers
+    out1, st1 = _run(scorer, directed, data, samples, 1, 1, n)
+    assert list(st1.iters) == list(st.iters)
+    assert out1[0] == out[0] and out1[4] == out[4]
+    np.testing.assert_allclose(out1, out, rtol=1e-12, atol=1e-15)
+
+
+@pytest.mark.parametrize("directed", [False, True])
+def test_stored_and_recompute_regimes_agree(scorer, directed):
+    n = 3001
+    data = planted_partition(n, k=9, d=40, seed=77, directed=directed, weighted=True)
+    samples = dv.draw_samples(data[0], data[1], n, 3000, 42, directed, True)
+    a, sa = _run(scorer, directed, data, samples, 2, 1, n)
+    b, sb = _run(scorer, directed, data, samples, 2, 2, n)
+    assert sa.regime == 1 and sb.regime == 2 and sb.matrix_bytes == 0
+    assert list(sa.iters) == list(sb.iters) and a[0] == b[0] and a[4] == b[4]
+    np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(np.array(list(sb.div)), np.array(list(sa.div)), rtol=1e-11,
+                               equal_nan=True)
+
+
+def test_q_matrix_symmetric_and_in_range_at_scale(scorer):
+    n = 2500
+    data = planted_partition(n, k=6, d=24, seed=5)
+    dv.wGCL(data[0], data[1], data[3], data[4], np.zeros(n), data[2], *EMPTY, False, 42, 0, False,
+            samples=None, scorer=scorer, max_alphas=1)
+    q = scorer.debug_read(0, n)
+    assert np.array_equal(q, q.T)
+    assert q.min() == 0.0 and q.max() == 1.0 and np.all(np.diag(q) == 1.0)
+    emb = data[4]
+    i, j = np.random.default_rng(0).integers(0, n, size=(2, 2000))
+    d = np.sqrt(((emb[i] - emb[j]) ** 2).sum(1))
+    sq = ((emb ** 2).sum(1))
+    D2 = sq[:, None] + sq[None, :] - 2 * emb @ emb.T
+    hi = np.sqrt(D2.max())
+    want = (1 - d / hi) ** 0.25
+    ok = i != j
+    np.testing.assert_allclose(q[i[ok], j[ok]], want[ok], rtol=1e-7, atol=1e-9)
