@@ -48,7 +48,7 @@ class Stats(C.Structure):
         ("fp_sweeps", C.c_int64), ("b_sweeps", C.c_int64),
         ("matrix_bytes", C.c_int64), ("launches", C.c_int64),
         ("n_tiles", C.c_int32), ("grid", C.c_int32), ("driver", C.c_int32),
-        ("n_ranks", C.c_int32), ("regime", C.c_int32), ("reserved", C.c_int32),
+        ("n_ranks", C.c_int32), ("regime", C.c_int32), ("diam_candidate_tiles", C.c_int32),
         ("ms_upload", C.c_float), ("ms_build", C.c_float), ("ms_solve", C.c_float),
         ("ms_total", C.c_float), ("ms_sweeps", C.c_float), ("ms_bsweeps", C.c_float),
     ]

@@ -107,13 +107,16 @@ template <bool STORE>
 __global__ void __launch_bounds__(NTHREADS)
 k_build_dist(const double *__restrict__ emb, int dp, const double *__restrict__ diag, int n,
              const int2 *__restrict__ tile_ij, long long tile_begin, long long tile_end,
-             double *__restrict__ q, unsigned long long *lohi) {
+             double *__restrict__ q, unsigned long long *lohi,
+             const int *__restrict__ tile_list = nullptr) {
     __shared__ double sA[TILE][DK + 1];
     __shared__ double sB[TILE][DK + 1];
     __shared__ double s_mn[NWARPS], s_mx[NWARPS];
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     double lmin = INFINITY, lmax = 0.0;
-    for (long long t = tile_begin + blockIdx.x; t < tile_end; t += gridDim.x) {
+    for (long long idx = tile_begin + blockIdx.x; idx < tile_end; idx += gridDim.x) {
+        // with a tile list (diameter verification) [tile_begin, tile_end) indexes the list
+        const long long t = tile_list ? (long long)tile_list[idx] : idx;
         const int2 ij = tile_ij[t];
         const int bi = ij.x, bj = ij.y;
         double acc[8][8];
@@ -536,6 +539,10 @@ struct cge_b200_handle {
     // device
     DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
         sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out, fpres;
+    // tensor-core diameter filter (landmark mode, large original graphs)
+    DevBuf diam_strips, diam_packed, diam_norms, diam_tilemax, diam_list, diam_ctr;
+    int diam_n_strips = 0;
+    bool diam_ok = false;
     DevBuf s_pda, s_pdb, s_nda, s_ndb, s_pa, s_pb, s_na, s_nb, s_pw, s_pw0a, s_pwla, s_pw0b, s_pwlb, s_nw0a, s_nwla, s_nw0b,
         s_nwlb, s_pq, s_nq;
     float ms_upload = 0.f;
@@ -797,6 +804,28 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         std::vector<int2> tij = make_tile_table(h->nbf);
         if ((rc = upload_vec(h->tile_ij_full, tij.data(), tij.size() * sizeof(int2), st)))
             return rc;
+        // the diameter of a large original graph goes through the tensor-core filter
+        // (cge_diameter.cu): runs of <= 64 tiles of one tile row are the work units
+        int64_t diam_min = 8192;
+        if (const char *e = getenv("CGE_B200_DIAM_MIN")) diam_min = atoll(e);
+        h->diam_ok = h->n_full >= diam_min && dp <= 128 && h->n_tiles_full < ((int64_t)1 << 31);
+        if (h->diam_ok) {
+            std::vector<int4> strips;
+            for (int64_t bi = 0; bi < h->nbf; ++bi)
+                for (int64_t bj = bi; bj < h->nbf; bj += 64)
+                    strips.push_back(make_int4((int)bi, (int)bj, (int)std::min<int64_t>(64, h->nbf - bj),
+                                               (int)tile_index(h->nbf, bi, bj)));
+            h->diam_n_strips = (int)strips.size();
+            if ((rc = upload_vec(h->diam_strips, strips.data(), strips.size() * sizeof(int4), st)))
+                return rc;
+            const size_t opb = (size_t)(dp / 16) * 4096;
+            if ((rc = h->diam_packed.ensure((size_t)h->nbf * 2 * opb))) return rc;
+            if ((rc = h->diam_norms.ensure((size_t)h->npf * 4))) return rc;
+            if ((rc = h->diam_tilemax.ensure((size_t)h->n_tiles_full * 4))) return rc;
+            if ((rc = h->diam_list.ensure((size_t)(1 << 20) * 4))) return rc;
+            if ((rc = h->diam_ctr.ensure(64))) return rc;
+            CUDA_TRY(cudaStreamSynchronize(st));  // strips is a local
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     // sampled pairs: (da,db) = vertices whose embedding rows give the distance (original graph in
@@ -885,6 +914,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     std::memset(&S, 0, sizeof(S));
     S.struct_size = (int32_t)sizeof(cge_b200_stats);
     for (int a = 0; a < CGE_B200_N_ALPHA; ++a) S.div[a] = S.auc[a] = NAN;
+    S.diam_candidate_tiles = -1;
     S.n = h->n;
     S.n_pairs = h->n * (h->n + 1) / 2;
     S.n_ranks = h->n_ranks;
@@ -994,10 +1024,52 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         if (h->landmark) {
             const int gridf = (int)std::max<int64_t>(
                 1, std::min<int64_t>(h->n_tiles_full, (int64_t)2 * h->sm_count));
-            k_build_dist<false><<<gridf, NTHREADS, 0, st>>>(
-                h->emb_full.as<double>(), dp, nullptr, (int)h->n_full, h->tile_ij_full.as<int2>(),
-                0, h->n_tiles_full, nullptr, lohi + 2);
-            ++h->launches;
+            bool exact_all = true;
+            S.diam_candidate_tiles = -1;
+            if (h->diam_ok) {
+                // tensor-core filter, then FP64 verification of the candidate tiles only
+                unsigned *ctr = h->diam_ctr.as<unsigned>();  // [0] strip counter [1] gmax [2] rmax [3] count
+                CUDA_TRY(cudaMemsetAsync(ctr, 0, 64, st));
+                launch_pack_bf16(h->emb_full.as<double>(), dp, (int)h->n_full, (int)h->d, (int)h->nbf,
+                                 h->diam_packed.as<unsigned char>(), h->diam_norms.as<float>(),
+                                 ctr + 2, st);
+                DiamArgs da;
+                da.packed = h->diam_packed.as<unsigned char>();
+                da.norms = h->diam_norms.as<float>();
+                da.nb = (int)h->nbf;
+                da.ksteps = dp / 16;
+                da.strips = h->diam_strips.as<int4>();
+                da.n_strips = h->diam_n_strips;
+                da.strip_counter = ctr;
+                da.tile_max = h->diam_tilemax.as<float>();
+                da.gmax_bits = ctr + 1;
+                CUDA_TRY(launch_diameter_filter(da, std::min(h->diam_n_strips, h->sm_count), st));
+                float rel = 1e-3f;
+                if (const char *e = getenv("CGE_B200_DIAM_REL")) rel = (float)atof(e);
+                const int cap = 1 << 20;
+                launch_select_candidates(da.tile_max, h->n_tiles_full, ctr + 1, ctr + 2, rel,
+                                         h->diam_list.as<int>(), cap, (int *)(ctr + 3), st);
+                h->launches += 3;
+                unsigned hc[4];
+                CUDA_TRY(cudaMemcpyAsync(hc, ctr, 16, cudaMemcpyDeviceToHost, st));
+                CUDA_TRY(cudaStreamSynchronize(st));
+                const int64_t cand = (int)hc[3];
+                S.diam_candidate_tiles = (int32_t)cand;
+                if (cand > 0 && cand <= cap && cand * 8 <= h->n_tiles_full) {
+                    const int gridc = (int)std::max<int64_t>(1, std::min<int64_t>(cand, 2 * h->sm_count));
+                    k_build_dist<false><<<gridc, NTHREADS, 0, st>>>(
+                        h->emb_full.as<double>(), dp, nullptr, (int)h->n_full,
+                        h->tile_ij_full.as<int2>(), 0, cand, nullptr, lohi + 2, h->diam_list.as<int>());
+                    ++h->launches;
+                    exact_all = false;
+                }
+            }
+            if (exact_all) {
+                k_build_dist<false><<<gridf, NTHREADS, 0, st>>>(
+                    h->emb_full.as<double>(), dp, nullptr, (int)h->n_full, h->tile_ij_full.as<int2>(),
+                    0, h->n_tiles_full, nullptr, lohi + 2);
+                ++h->launches;
+            }
         }
         const double *e = h->landmark ? h->emb_full.as<double>() : h->emb.as<double>();
         const double *dg = h->landmark ? nullptr : h->dist.as<double>();
@@ -1381,7 +1453,8 @@ void cge_b200_destroy(cge_b200_handle *h) {
     for (DevBuf *b :
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
-          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
+          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
+          &h->diam_list, &h->diam_ctr, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
           &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})
         b->release();

@@ -688,6 +688,24 @@ size_t fp_ring_smem_bytes(int directed);
 // stored regime with a run-time exponent (small problems): kind as in launch_tiles
 void launch_tiles_rt(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 const void *fp_kernel_rt(int directed);
+// tensor-core diameter filter (cge_diameter.cu)
+struct DiamArgs {
+    const unsigned char *packed;  // per 128-row block: hi part then lo part, each ksteps*4096 B
+    const float *norms;           // [nb*128] squared norms, a large negative value on pads
+    int nb, ksteps;               // blocks; dp/16
+    const int4 *strips;           // (bi, bj0, count, first tile index): runs of tiles in one tile row
+    int n_strips;
+    unsigned *strip_counter;
+    float *tile_max;              // [n_tiles] largest approximate d^2 of each tile
+    unsigned *gmax_bits;          // bit pattern of the largest approximate d^2 (non-negative float)
+};
+size_t diameter_smem_bytes(int ksteps);
+void launch_pack_bf16(const double *emb, int dp, int n, int d_true, int nb, unsigned char *packed,
+                      float *norms, unsigned *rmax_bits, cudaStream_t st);
+cudaError_t launch_diameter_filter(const DiamArgs &a, int grid, cudaStream_t st);
+void launch_select_candidates(const float *tile_max, long long n_tiles, const unsigned *gmax_bits,
+                              const unsigned *rmax_bits, float rel, int *list, int cap, int *count,
+                              cudaStream_t st);
 // recompute regime (cge_recompute.cu): kind as in launch_tiles, exponent taken from a.m
 void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 const void *fp_kernel_rc(int directed);

@@ -119,7 +119,9 @@ typedef struct cge_b200_stats {
     int64_t matrix_bytes;                   /* bytes of the stored q matrix */
     int64_t launches;                       /* kernels launched by this library in the call */
     int32_t n_tiles, grid, driver, n_ranks;
-    int32_t regime, reserved;               /* regime actually used */
+    int32_t regime;                         /* regime actually used */
+    int32_t diam_candidate_tiles;           /* landmark mode: tiles re-checked in FP64 after the
+                                               tensor-core diameter filter; -1 = filter not used */
     float ms_upload;                        /* H2D + host preprocessing */
     float ms_build;                         /* distance tiles + normalisation (CUDA events) */
     float ms_solve;                         /* the alpha loop (CUDA events) */

@@ -49,7 +49,7 @@ mutable struct Stats
     iters::NTuple{N_ALPHA,Int32}; div::NTuple{N_ALPHA,Float64}; auc::NTuple{N_ALPHA,Float64}
     lo::Float64; hi::Float64; hi_full::Float64
     n::Int64; n_pairs::Int64; fp_sweeps::Int64; b_sweeps::Int64; matrix_bytes::Int64; launches::Int64
-    n_tiles::Int32; grid::Int32; driver::Int32; n_ranks::Int32; regime::Int32; reserved::Int32
+    n_tiles::Int32; grid::Int32; driver::Int32; n_ranks::Int32; regime::Int32; diam_candidate_tiles::Int32
     ms_upload::Float32; ms_build::Float32; ms_solve::Float32; ms_total::Float32
     ms_sweeps::Float32; ms_bsweeps::Float32
     Stats() = new(0, 0, ntuple(_ -> Int32(0), N_ALPHA), ntuple(_ -> NaN, N_ALPHA),

@@ -80,3 +80,32 @@ def test_q_matrix_symmetric_and_in_range_at_scale(scorer):
     want = (1 - d / hi) ** 0.25
     ok = i != j
     np.testing.assert_allclose(q[i[ok], j[ok]], want[ok], rtol=1e-7, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,d,k", [(3001, 40, 9), (5000, 128, 16), (700, 7, 3)])
+def test_tensor_core_diameter_filter_is_exact(scorer, monkeypatch, n, d, k):
+    """Landmark mode needs the exact diameter of the ORIGINAL graph (divergence.jl:113).  The
+    tcgen05 filter + FP64 verification must return the very same double as the all-FP64 pass, and
+    only a small share of the tiles may need verification."""
+    from cge_jl_b200.landmarks import landmarks, split_cluster_rss
+    from util import clusters_of
+    edges, ew, vw, comm, emb = planted_partition(n, k=k, d=d, seed=n + d)
+    emb[17] *= 1.5  # an outlier row pair decides the diameter
+    lm = landmarks(edges, ew, vw, clusters_of(comm), comm, emb, False, 4 * k, 4, split_cluster_rss,
+                   False)
+    dii, lemb, lcomm, ledges, lw, lweight, v2l = lm
+    samples = dv.draw_samples(edges, ew, n, 2000, 42, False, False)
+    res = {}
+    for label, dmin in (("fp64", "1000000000"), ("filter", "0")):
+        monkeypatch.setenv("CGE_B200_DIAM_MIN", dmin)
+        out, st = dv.wGCL(ledges, lw, lcomm, lemb, dii, lweight, vw, v2l, edges, ew, emb, False, 42,
+                          2000, False, samples=samples, return_stats=True, scorer=scorer)
+        res[label] = (out, float(st.hi_full), int(st.diam_candidate_tiles), int(st.launches))
+    assert res["fp64"][2] == -1 and res["filter"][2] >= 1
+    nb = (n + 127) // 128
+    assert res["filter"][2] <= max(4, nb * (nb + 1) // 2 // 8)
+    assert res["filter"][1] == res["fp64"][1]                      # bit-identical diameter
+    assert np.array_equal(res["filter"][0], res["fp64"][0])
+    D2 = ((emb[:, None, :] - emb[None, :, :]) ** 2).sum(-1) if n <= 3001 else None
+    if D2 is not None:
+        assert np.isclose(res["filter"][1], np.sqrt(D2.max()), rtol=1e-14)
