@@ -26,6 +26,9 @@ KEYS = [
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "sm__sass_inst_executed_op_global_ld.sum", "sm__sass_inst_executed_op_shared_ld.sum",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active",
 ]
 
 

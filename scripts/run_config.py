@@ -25,6 +25,7 @@ from cge_jl_b200 import divergence as dv  # noqa: E402
 from cge_jl_b200.landmarks import landmarks, split_cluster_rss  # noqa: E402
 from cge_jl_b200.synth import planted_partition  # noqa: E402
 
+LANDMARKS = 0
 EMPTY = (np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int64), np.zeros(0),
          np.zeros((0, 0)))
 
@@ -38,6 +39,13 @@ def build(cfg):
         edges, ew, vw, comm, emb = planted_partition(n, k=k, d=d, seed=7, directed=directed,
                                                      weighted=directed)
         name = f"synthetic planted partition n={n} d={d} k={k} directed={directed}"
+        if LANDMARKS > 0:
+            by = {}
+            for v, c in enumerate(comm[:, 0], start=1):
+                by.setdefault(int(c), []).append(v)
+            lm = landmarks(edges, ew, vw, [np.asarray(v) for v in by.values()], comm, emb, False,
+                           LANDMARKS, 4, split_cluster_rss, directed)
+            name += f" landmarks -l {LANDMARKS}"
     elif cfg in (1, 2):
         z = np.load(os.path.join(ROOT, "tests", "golden", "example10k.npz"))
         edges, ew, vw, comm, emb = (z[k] for k in ("edges", "eweights", "vweights", "comm", "embedding"))
@@ -78,6 +86,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=0)
     ap.add_argument("--synthetic", default="", help="n,d,k,directed instead of --config")
+    ap.add_argument("--landmarks", type=int, default=0, help="with --synthetic: landmark mode, -l L")
     ap.add_argument("--samples", type=int, default=10000)
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--regime", type=int, default=0)
@@ -92,6 +101,8 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    global LANDMARKS
+    LANDMARKS = args.landmarks
     c = build(args.synthetic or args.config)
     n = c["vw"].shape[0]
     t0 = time.perf_counter()
@@ -101,7 +112,7 @@ def main():
         n_scored, target = n, c["vw"]
     else:
         dii, lemb, lcomm, ledges, lw, lweight, v2l = c["lm"]
-        samples = dv.draw_samples(c["edges"], c["ew"], n, args.samples, 42, False, False)
+        samples = dv.draw_samples(c["edges"], c["ew"], n, args.samples, 42, c["directed"], False)
         prob = (ledges, lw, lcomm, lemb, dii, lweight, c["vw"], v2l, c["emb"])
         n_scored, target = lemb.shape[0], lweight
     t_sample = time.perf_counter() - t0
