@@ -29,8 +29,10 @@ constexpr float DM_PAD_NORM = -1e30f;
 // ---- packing: FP64 rows -> BF16 hi/lo in the canonical K-major no-swizzle UMMA layout ----------
 // core matrix = 8 rows x 16 bytes (8 BF16 along K), stored as 128 contiguous bytes; within one
 // operand part: offset(kc, rg, r) = ((kc*16 + rg)*8 + r)*16 with kc = k/8, rg = row/8, r = row%8.
-__global__ void k_pack_bf16(const double *__restrict__ emb, int dp, int n, int d_true,
-                            long long n_rows, unsigned char *__restrict__ packed,
+// The rows are centred first (x - mean; distances are translation invariant): the filter's error
+// bound scales with the largest squared norm, which must not be inflated by a common offset.
+__global__ void k_pack_bf16(const double *__restrict__ emb, const double *__restrict__ mean, int dp,
+                            int n, int d_true, long long n_rows, unsigned char *__restrict__ packed,
                             float *__restrict__ norms, unsigned *rmax_bits) {
     const int ksteps = dp / 16, kchunks = dp / 8;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -44,7 +46,8 @@ __global__ void k_pack_bf16(const double *__restrict__ emb, int dp, int n, int d
     __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const double x = row < n ? emb[(size_t)row * dp + kc * 8 + e] : 0.0;
+        const int c = kc * 8 + e;
+        const double x = (row < n && c < d_true) ? emb[(size_t)row * dp + c] - mean[c] : 0.0;
         hi[e] = __float2bfloat16_rn((float)x);
         lo[e] = __float2bfloat16_rn((float)(x - (double)__bfloat162float(hi[e])));
     }
@@ -55,7 +58,7 @@ __global__ void k_pack_bf16(const double *__restrict__ emb, int dp, int n, int d
         if (row < n) {
             double s = 0.0;
             for (int c = 0; c < d_true; ++c) {
-                const double x = emb[(size_t)row * dp + c];
+                const double x = emb[(size_t)row * dp + c] - mean[c];
                 s = fma(x, x, s);
             }
             nf = (float)s;
@@ -251,11 +254,11 @@ __global__ void k_select_candidates(const float *__restrict__ tile_max, long lon
 
 size_t diameter_smem_bytes(int ksteps) { return 6 * (size_t)ksteps * 4096 + 3 * TILE * 4 + 128; }
 
-void launch_pack_bf16(const double *emb, int dp, int n, int d_true, int nb, unsigned char *packed,
-                      float *norms, unsigned *rmax_bits, cudaStream_t st) {
+void launch_pack_bf16(const double *emb, const double *mean, int dp, int n, int d_true, int nb,
+                      unsigned char *packed, float *norms, unsigned *rmax_bits, cudaStream_t st) {
     const long long threads = (long long)nb * TILE * (dp / 8);
     k_pack_bf16<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(
-        emb, dp, n, d_true, (long long)nb * TILE, packed, norms, rmax_bits);
+        emb, mean, dp, n, d_true, (long long)nb * TILE, packed, norms, rmax_bits);
 }
 
 cudaError_t launch_diameter_filter(const DiamArgs &a, int grid, cudaStream_t st) {

@@ -540,7 +540,7 @@ struct cge_b200_handle {
     DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
         sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out, fpres;
     // tensor-core diameter filter (landmark mode, large original graphs)
-    DevBuf diam_strips, diam_packed, diam_norms, diam_tilemax, diam_list, diam_ctr;
+    DevBuf diam_strips, diam_packed, diam_norms, diam_tilemax, diam_list, diam_ctr, diam_mean;
     int diam_n_strips = 0;
     bool diam_ok = false;
     DevBuf s_pda, s_pdb, s_nda, s_ndb, s_pa, s_pb, s_na, s_nb, s_pw, s_pw0a, s_pwla, s_pw0b, s_pwlb, s_nw0a, s_nwla, s_nw0b,
@@ -795,11 +795,15 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         h->nbf = (h->n_full + TILE - 1) / TILE;
         h->npf = h->nbf * TILE;
         h->n_tiles_full = h->nbf * (h->nbf + 1) / 2;
-        std::vector<double> ef((size_t)(h->npf * dp), 0.0);
+        std::vector<double> ef((size_t)(h->npf * dp), 0.0), mean((size_t)dp, 0.0);
         for (int64_t v = 0; v < h->n_full; ++v)
-            for (int64_t c = 0; c < p->d; ++c)
-                ef[(size_t)(v * dp + c)] =
-                    p->init_embed[v * p->init_row_stride + c * p->init_col_stride];
+            for (int64_t c = 0; c < p->d; ++c) {
+                const double x = p->init_embed[v * p->init_row_stride + c * p->init_col_stride];
+                ef[(size_t)(v * dp + c)] = x;
+                mean[(size_t)c] += x;
+            }
+        for (int64_t c = 0; c < p->d; ++c) mean[(size_t)c] /= (double)h->n_full;
+        if ((rc = upload_vec(h->diam_mean, mean.data(), mean.size() * 8, st))) return rc;
         if ((rc = upload_vec(h->emb_full, ef.data(), ef.size() * 8, st))) return rc;
         std::vector<int2> tij = make_tile_table(h->nbf);
         if ((rc = upload_vec(h->tile_ij_full, tij.data(), tij.size() * sizeof(int2), st)))
@@ -1030,7 +1034,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 // tensor-core filter, then FP64 verification of the candidate tiles only
                 unsigned *ctr = h->diam_ctr.as<unsigned>();  // [0] strip counter [1] gmax [2] rmax [3] count
                 CUDA_TRY(cudaMemsetAsync(ctr, 0, 64, st));
-                launch_pack_bf16(h->emb_full.as<double>(), dp, (int)h->n_full, (int)h->d, (int)h->nbf,
+                launch_pack_bf16(h->emb_full.as<double>(), h->diam_mean.as<double>(), dp,
+                                 (int)h->n_full, (int)h->d, (int)h->nbf,
                                  h->diam_packed.as<unsigned char>(), h->diam_norms.as<float>(),
                                  ctr + 2, st);
                 DiamArgs da;
@@ -1454,7 +1459,7 @@ void cge_b200_destroy(cge_b200_handle *h) {
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
           &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
-          &h->diam_list, &h->diam_ctr, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
+          &h->diam_list, &h->diam_ctr, &h->diam_mean, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
           &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})
         b->release();

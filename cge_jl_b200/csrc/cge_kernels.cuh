@@ -700,8 +700,8 @@ struct DiamArgs {
     unsigned *gmax_bits;          // bit pattern of the largest approximate d^2 (non-negative float)
 };
 size_t diameter_smem_bytes(int ksteps);
-void launch_pack_bf16(const double *emb, int dp, int n, int d_true, int nb, unsigned char *packed,
-                      float *norms, unsigned *rmax_bits, cudaStream_t st);
+void launch_pack_bf16(const double *emb, const double *mean, int dp, int n, int d_true, int nb,
+                      unsigned char *packed, float *norms, unsigned *rmax_bits, cudaStream_t st);
 cudaError_t launch_diameter_filter(const DiamArgs &a, int grid, cudaStream_t st);
 void launch_select_candidates(const float *tile_max, long long n_tiles, const unsigned *gmax_bits,
                               const unsigned *rmax_bits, float rel, int *list, int cap, int *count,

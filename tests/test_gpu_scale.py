@@ -109,3 +109,22 @@ def test_tensor_core_diameter_filter_is_exact(scorer, monkeypatch, n, d, k):
     D2 = ((emb[:, None, :] - emb[None, :, :]) ** 2).sum(-1) if n <= 3001 else None
     if D2 is not None:
         assert np.isclose(res["filter"][1], np.sqrt(D2.max()), rtol=1e-14)
+
+
+def test_diameter_filter_with_a_large_common_offset(scorer, monkeypatch):
+    """A common offset of the embedding inflates the norms but not the distances: the packed copy
+    is centred, so the filter still prunes and the diameter stays exact."""
+    from cge_jl_b200.landmarks import landmarks, split_cluster_rss
+    from util import clusters_of
+    n = 2000
+    edges, ew, vw, comm, emb = planted_partition(n, k=5, d=32, seed=3)
+    emb = emb + 1000.0
+    lm = landmarks(edges, ew, vw, clusters_of(comm), comm, emb, False, 20, 4, split_cluster_rss, False)
+    dii, lemb, lcomm, ledges, lw, lweight, v2l = lm
+    samples = dv.draw_samples(edges, ew, n, 500, 42, False, False)
+    monkeypatch.setenv("CGE_B200_DIAM_MIN", "0")
+    out, st = dv.wGCL(ledges, lw, lcomm, lemb, dii, lweight, vw, v2l, edges, ew, emb, False, 42, 500,
+                      False, samples=samples, return_stats=True, scorer=scorer)
+    D2 = ((emb[:, None, :] - emb[None, :, :]) ** 2).sum(-1)
+    assert np.isclose(st.hi_full, np.sqrt(D2.max()), rtol=1e-12)
+    assert 1 <= st.diam_candidate_tiles <= 16
