@@ -125,6 +125,8 @@ def run_reference(args):
     if rank != 0:
         return
     w = workload(1 if args.gpus == 1 else args.gpus)
+    if args.gpus > 1:
+        args.ref_alphas = 1  # the weak-scaling graphs are N times larger: keep a step under a minute
     vals, times = [], []
     t_start = time.perf_counter()
     budget_s = 240.0  # the whole reference arm must end within a few minutes
