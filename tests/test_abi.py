@@ -90,3 +90,28 @@ def test_shard_plan_partitions_the_tile_sequence(n, world):
         prev_end = e
         assert abs((e - b) - nt / world) <= 1
     assert prev_end == nt
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No silent fallback when libcge_b200.so has not been built."""
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libcge_b200.so"))
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load()
+    from cge_jl_b200 import divergence as dv
+    with pytest.raises(ImportError):
+        dv.Scorer(0)
+
+
+def test_score_multi_rejects_bad_requests():
+    lib = _lib.load()
+    p = _lib.Problem()
+    out = np.zeros(7)
+    n_out = C.c_int32()
+    rc = lib.cge_b200_score_multi(C.byref(p), 1, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                  C.byref(n_out), None)
+    assert rc == _lib.ERR_ARG and "2..8" in _lib.last_error()
+    if lib.cge_b200_device_count() == 0:
+        rc = lib.cge_b200_score_multi(C.byref(p), 2, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                      C.byref(n_out), None)
+        assert rc == _lib.ERR_CUDA
