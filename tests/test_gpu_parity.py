@@ -310,3 +310,21 @@ def test_run_is_bit_reproducible(scorer):
     dv.wGCL(edges, ew, comm, emb, np.zeros(700), vw, *EMPTY, False, 42, 1000, False,
             samples=samples, scorer=scorer)
     assert np.array_equal(T, scorer.debug_read(1, 700))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_graphs(scorer, seed):
+    """Randomised parity sweep: size, dimension, community count, weights, direction, split flag and
+    driver all vary with the seed; every case must meet the full parity bars against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(20, 420))
+    k = int(rng.integers(1, min(n // 4, 30) + 1))
+    d = int(rng.integers(2, 70))
+    directed = bool(seed % 2)
+    edges, ew, vw, comm, emb = planted_partition(n, k, d, seed=seed, directed=directed,
+                                                 weighted=bool(rng.integers(0, 2)),
+                                                 deg=int(rng.integers(4, 12)))
+    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
+                                   split=bool(rng.integers(0, 2)), K=int(rng.integers(50, 1500)),
+                                   driver=int(rng.integers(1, 4)), regime=int(rng.integers(1, 3)))
+    assert_parity(out, stats, ref, tr)
