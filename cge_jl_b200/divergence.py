@@ -42,26 +42,30 @@ def _pi(a):
 # ---------------------------------------------------------------------------------------------
 # sampling (host side of the boundary)
 # ---------------------------------------------------------------------------------------------
-def _sample_non_edges(rng, n, codes_sorted, K, directed):
+def _sample_non_edges(rng, n, codes, K, directed):
     """K pairs drawn uniformly with replacement from NE (divergence.jl:121-137 / 405-421):
     unordered i<j (ordered i!=j when directed) that are not in the edge set.  The reference
     materialises NE and indexes it; rejection sampling draws from the same distribution without
-    the O(n^2) array."""
+    the O(n^2) array.  ``codes`` = i*(n+1)+j of every edge (unsorted, duplicates allowed); only the
+    few thousand candidates are sorted, the edge list is scanned once per round."""
     n_pairs = n * (n - 1) if directed else n * (n - 1) // 2
-    ci, cj = codes_sorted // (n + 1), codes_sorted % (n + 1)
-    n_ne = n_pairs - int(np.count_nonzero(ci != cj))
-    if n_ne <= 0:
+    if n_pairs - codes.shape[0] * 8 < 0 and n <= 5000:
+        # possibly dense: count exactly and enumerate NE like the reference does
+        uniq = np.unique(codes)
+        n_ne = n_pairs - int(np.count_nonzero(uniq // (n + 1) != uniq % (n + 1)))
+        if n_ne <= 0:
+            raise ValueError("collection must be non-empty: the graph has no non-edges to sample "
+                             "(divergence.jl:137 leaves NE empty)")
+        if n_ne * 8 < n_pairs:
+            ii, jj = np.meshgrid(np.arange(1, n + 1), np.arange(1, n + 1), indexing="ij")
+            keep = (ii != jj) if directed else (ii < jj)
+            ii, jj = ii[keep], jj[keep]
+            free = ~np.isin(ii * (n + 1) + jj, uniq)
+            pick = rng.integers(0, int(free.sum()), size=K)
+            return ii[free][pick], jj[free][pick]
+    elif n_pairs <= codes.shape[0] and n_pairs - np.unique(codes).shape[0] <= 0:
         raise ValueError("collection must be non-empty: the graph has no non-edges to sample "
                          "(divergence.jl:137 leaves NE empty)")
-    if n_ne * 8 < n_pairs and n <= 5000:
-        # dense graph: rejection would spin; enumerate NE like the reference does
-        ii, jj = np.meshgrid(np.arange(1, n + 1), np.arange(1, n + 1), indexing="ij")
-        keep = (ii != jj) if directed else (ii < jj)
-        ii, jj = ii[keep], jj[keep]
-        code = ii * (n + 1) + jj
-        free = ~np.isin(code, codes_sorted)
-        pick = rng.integers(0, int(free.sum()), size=K)
-        return ii[free][pick], jj[free][pick]
     out_i = np.empty(K, dtype=np.int64)
     out_j = np.empty(K, dtype=np.int64)
     got = 0
@@ -71,12 +75,11 @@ def _sample_non_edges(rng, n, codes_sorted, K, directed):
         j = rng.integers(1, n + 1, size=need)
         if not directed:
             i, j = np.minimum(i, j), np.maximum(i, j)
-        ok = i != j
         code = i * (n + 1) + j
-        if codes_sorted.size:
-            pos = np.searchsorted(codes_sorted, code)
-            pos[pos >= codes_sorted.shape[0]] = 0
-            ok &= codes_sorted[pos] != code
+        ok = i != j
+        if codes.size:
+            hit = codes[np.isin(codes, code)]       # the candidates that are edges
+            ok &= ~np.isin(code, hit)
         i, j = i[ok][: K - got], j[ok][: K - got]
         out_i[got: got + i.shape[0]] = i
         out_j[got: got + i.shape[0]] = j
@@ -102,7 +105,7 @@ def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact):
         e_i, e_j = adj_edges[:, 0], adj_edges[:, 1]
     else:
         e_i, e_j = adj_edges.min(axis=1), adj_edges.max(axis=1)  # divergence.jl:133
-    codes = np.unique(e_i * (adj_n + 1) + e_j)
+    codes = e_i * (adj_n + 1) + e_j
     n_sets = 1 if seed != -1 else N_ALPHA
     pi = np.empty((n_sets, K), dtype=np.int64)
     pj = np.empty_like(pi)
