@@ -279,7 +279,7 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
 //   Sout_i += Tin_j * Tout_i * g     Sout_j += Tin_i * Tout_j * g
 // partA collects the Sin sums without their own Tin factor, partB the Sout sums without Tout.
 // The second copy of the diagonal term (i == j is added twice at :444-447) is added by the
-// finalize kernel.  Two batches of 8 rows at two CTAs per SM: a single 16-row loop with 32 row
+// finalize kernel.  Four batches of 4 rows at two CTAs per SM; a single 16-row loop with 32 row
 // accumulators needs 255 registers (one CTA per SM) and measured slower (config 3: 2.32 ms per
 // pass against 2.00).
 // ---------------------------------------------------------------------------------------------
@@ -299,20 +299,35 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
     const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
     double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0;  // Sin column sums  (Tout_r * g)
     double co0 = 0.0, co1 = 0.0, co2 = 0.0, co3 = 0.0;  // Sout column sums (Tin_r * g)
+    // four batches of four rows, the loads of the next batch issued before the current one is
+    // consumed (register double buffering, as in tile_bpass)
+    constexpr int BR = 4, NBAT = ROWS_PER_WARP / BR;
+    double2 v01[2][BR], v23[2][BR];
 #pragma unroll
-    for (int batch = 0; batch < 2; ++batch) {
-        double rin[8], rout[8];
+    for (int r4 = 0; r4 < BR; ++r4) {
+        v01[0][r4] = ld_stream(base + r4 * (TILE / 2) + lane, pol);
+        v23[0][r4] = ld_stream(base + r4 * (TILE / 2) + 32 + lane, pol);
+    }
 #pragma unroll
-        for (int r8 = 0; r8 < 8; ++r8) {
-            const int rr = batch * 8 + r8;
-            const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
-            const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
+    for (int batch = 0; batch < NBAT; ++batch) {
+        const int cb = batch & 1, nx = cb ^ 1;
+        if (batch + 1 < NBAT) {
+#pragma unroll
+            for (int r4 = 0; r4 < BR; ++r4) {
+                v01[nx][r4] = ld_stream(base + ((batch + 1) * BR + r4) * (TILE / 2) + lane, pol);
+                v23[nx][r4] = ld_stream(base + ((batch + 1) * BR + r4) * (TILE / 2) + 32 + lane, pol);
+            }
+        }
+        double rin[BR], rout[BR];
+#pragma unroll
+        for (int r4 = 0; r4 < BR; ++r4) {
+            const int rr = batch * BR + r4;
             const double t_in = __shfl_sync(FULL, trow_in, rr);
             const double t_out = __shfl_sync(FULL, trow_out, rr);
-            const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
-            const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
-            rin[r8] = fma(g3, to23.y, fma(g2, to23.x, fma(g1, to01.y, g0 * to01.x)));
-            rout[r8] = fma(g3, ti23.y, fma(g2, ti23.x, fma(g1, ti01.y, g0 * ti01.x)));
+            const double g0 = powm_any<M>(v01[cb][r4].x, a.m), g1 = powm_any<M>(v01[cb][r4].y, a.m);
+            const double g2 = powm_any<M>(v23[cb][r4].x, a.m), g3 = powm_any<M>(v23[cb][r4].y, a.m);
+            rin[r4] = fma(g3, to23.y, fma(g2, to23.x, fma(g1, to01.y, g0 * to01.x)));
+            rout[r4] = fma(g3, ti23.y, fma(g2, ti23.x, fma(g1, ti01.y, g0 * ti01.x)));
             ci0 = fma(t_out, g0, ci0);
             ci1 = fma(t_out, g1, ci1);
             ci2 = fma(t_out, g2, ci2);
@@ -322,11 +337,11 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
             co2 = fma(t_in, g2, co2);
             co3 = fma(t_in, g3, co3);
         }
-        warp_treduce<8>(rin, lane);
-        warp_treduce<8>(rout, lane);
-        if ((lane & 3) == 0) {
-            const size_t o = (size_t)bj * a.np + (size_t)bi * TILE + row0 + batch * 8 +
-                             treduce_index<8>(lane);
+        warp_treduce<BR>(rin, lane);
+        warp_treduce<BR>(rout, lane);
+        if ((lane & 7) == 0) {
+            const size_t o = (size_t)bj * a.np + (size_t)bi * TILE + row0 + batch * BR +
+                             treduce_index<BR>(lane);
             a.partA[o] = rin[0];
             a.partB[o] = rout[0];
         }
