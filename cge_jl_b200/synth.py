@@ -47,3 +47,41 @@ def planted_partition(n, k=64, d=32, degree=16, p_in=0.75, seed=0, directed=Fals
     mu = 0.5 * rng.normal(size=(k, d))
     emb = mu[comm0] + 0.7 * rng.normal(size=(n, d))
     return edges, w, vw, (comm0 + 1).reshape(-1, 1), emb
+
+
+def abcd_like(n, k=64, d=128, gamma=2.5, beta=1.5, dmin=5, dmax=50, xi=0.2, seed=0):
+    """ABCD-style undirected benchmark graph (BASELINE config 4): power-law degrees
+    (exponent ``gamma`` in [dmin, dmax]), power-law community sizes (exponent ``beta``), a fraction
+    ``xi`` of every vertex's edge stubs leaves its community.  Same return convention as
+    :func:`planted_partition`.  Vertices of a community are contiguous; sizes are very unequal,
+    which exercises community boundaries inside tiles and tiny / huge communities."""
+    rng = np.random.default_rng(seed)
+    # community sizes ~ s^-beta on [n/(8k), 4n/k], rescaled to sum to n, every community >= 2
+    lo, hi = max(2.0, n / (8.0 * k)), 4.0 * n / k
+    u = rng.random(k)
+    sizes = (lo ** (1 - beta) + u * (hi ** (1 - beta) - lo ** (1 - beta))) ** (1 / (1 - beta))
+    sizes = np.maximum(2, np.floor(sizes * n / sizes.sum())).astype(np.int64)
+    sizes[np.argmax(sizes)] += n - sizes.sum()
+    start = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    comm0 = np.repeat(np.arange(k, dtype=np.int64), sizes)
+    u = rng.random(n)
+    deg = (dmin ** (1 - gamma) + u * (dmax ** (1 - gamma) - dmin ** (1 - gamma))) ** (1 / (1 - gamma))
+    deg = np.floor(deg).astype(np.int64)
+    src = np.repeat(np.arange(n, dtype=np.int64), (deg + 1) // 2)  # each stub pair -> one edge
+    inside = rng.random(src.shape[0]) >= xi
+    v_in = start[comm0[src]] + (rng.random(src.shape[0]) * sizes[comm0[src]]).astype(np.int64)
+    v_out = rng.integers(0, n, size=src.shape[0])
+    dst = np.where(inside, v_in, v_out)
+    nxt = np.arange(n, dtype=np.int64) + 1          # ring per community: no isolated vertex
+    nxt[start + sizes - 1] = start
+    e = np.concatenate([np.stack([np.arange(n, dtype=np.int64), nxt], axis=1),
+                        np.stack([src, dst], axis=1)])
+    e = e[e[:, 0] != e[:, 1]]
+    e = np.unique(np.stack([e.min(axis=1), e.max(axis=1)], axis=1), axis=0)
+    w = np.ones(e.shape[0])
+    vw = np.zeros(n)
+    np.add.at(vw, e[:, 0], w)
+    np.add.at(vw, e[:, 1], w)
+    mu = 0.5 * rng.normal(size=(k, d))
+    emb = mu[comm0] + 0.7 * rng.normal(size=(n, d))
+    return e + 1, w, vw, (comm0 + 1).reshape(-1, 1), emb

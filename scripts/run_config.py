@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from cge_jl_b200 import divergence as dv  # noqa: E402
 from cge_jl_b200.landmarks import landmarks, split_cluster_rss  # noqa: E402
-from cge_jl_b200.synth import planted_partition  # noqa: E402
+from cge_jl_b200.synth import abcd_like, planted_partition  # noqa: E402
 
 LANDMARKS = 0
 EMPTY = (np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int64), np.zeros(0),
@@ -62,8 +62,8 @@ def build(cfg):
         directed = True
         name = "synthetic 50k-node weighted planted-partition digraph, d=64, k=32, exact, directed"
     elif cfg == 4:
-        edges, ew, vw, comm, emb = planted_partition(200000, k=64, d=128, seed=1004)
-        name = "synthetic 200k-node planted-partition graph, 64 communities, d=128, exact"
+        edges, ew, vw, comm, emb = abcd_like(200000, k=64, d=128, seed=1004)
+        name = "synthetic 200k-node ABCD-style graph, 64 communities, d=128, exact"
     elif cfg == 5:
         # the landmark half of BASELINE.json configs[4]: 1M vertices, d = 128, rss landmarks -l 4000
         # on one GPU (the exact half needs 4 TB of pairs: recompute regime at scale, not in round 1)

@@ -128,3 +128,26 @@ def test_diameter_filter_with_a_large_common_offset(scorer, monkeypatch):
     D2 = ((emb[:, None, :] - emb[None, :, :]) ** 2).sum(-1)
     assert np.isclose(st.hi_full, np.sqrt(D2.max()), rtol=1e-12)
     assert 1 <= st.diam_candidate_tiles <= 16
+
+
+def test_abcd_like_unequal_communities(scorer):
+    """ABCD-style input (BASELINE config 4's family): power-law degrees and very unequal community
+    sizes (2 .. thousands of vertices) -- community boundaries fall inside tiles everywhere."""
+    from cge_jl_b200.synth import abcd_like
+    n = 20011
+    data = abcd_like(n, k=64, d=32, seed=4)
+    edges, ew, vw = data[0], data[1], data[2]
+    samples = dv.draw_samples(edges, ew, n, 5000, 42, False, True)
+    out, st = _run(scorer, False, data, samples, 2, 1, n)
+    assert np.all(np.isfinite(out)) and st.n_alpha_run >= 6
+    assert np.abs(vw - scorer.debug_read(3, n)).max() <= 0.001
+    out1, st1 = _run(scorer, False, data, samples, 1, 1, n)
+    assert list(st1.iters) == list(st.iters)
+    np.testing.assert_allclose(out1, out, rtol=1e-12, atol=1e-15)
+    # the B matrix bins survive the irregular community layout: recompute regime agrees too
+    small = abcd_like(2500, k=40, d=16, seed=9)
+    s2 = dv.draw_samples(small[0], small[1], 2500, 2000, 42, False, True)
+    a, sa = _run(scorer, False, small, s2, 2, 1, 2500)
+    b, sb = _run(scorer, False, small, s2, 2, 2, 2500)
+    assert list(sa.iters) == list(sb.iters)
+    np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-15)
