@@ -1,6 +1,15 @@
 """``python -m cge_jl_b200 -g G -e E [-c C] [flags]`` -- the CGE_CLI.jl driver
 (/root/reference/example/CGE_CLI.jl:1-25) on top of the B200 scorer; same flags, same output."""
+import os
+
 import numpy as np
+
+# One-shot CLI process: CUDA's lazy module loading would pay for every kernel instantiation on its
+# first use inside the scoring call (0.39 s for the 10k example against 0.08 s when the library's
+# modules are loaded up front; measured with scripts/cold_start.py).  Must be set before the CUDA
+# runtime initialises; long-lived hosts that share the process with other CUDA libraries keep the
+# default.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 from . import landmarks, parseargs
 from .divergence import wGCL, wGCL_directed
