@@ -328,3 +328,34 @@ def test_random_small_graphs(scorer, seed):
                                    split=bool(rng.integers(0, 2)), K=int(rng.integers(50, 1500)),
                                    driver=int(rng.integers(1, 4)), regime=int(rng.integers(1, 3)))
     assert_parity(out, stats, ref, tr)
+
+
+def test_cli_end_to_end(tmp_path):
+    """`python -m cge_jl_b200` with the CGE_CLI.jl flags (example/CGE_CLI.jl:1-25): text files ->
+    parseargs -> landmarks -> scorer -> printed 7-vector, in a fresh process."""
+    import ast
+    import os
+    import subprocess
+    import sys
+    edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    (tmp_path / "g.edgelist").write_text("\n".join(f"{a - 1} {b - 1}" for a, b in edges))
+    (tmp_path / "g.ecg").write_text("\n".join(str(c - 1) for c in comm[:, 0]) + "\n")
+    (tmp_path / "g.emb").write_text(
+        "\n".join(" ".join([str(i)] + [repr(float(x)) for x in emb[i]]) for i in range(115)) + "\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [sys.executable, "-m", "cge_jl_b200", "-g", str(tmp_path / "g.edgelist"), "-c",
+            str(tmp_path / "g.ecg"), "-e", str(tmp_path / "g.emb"), "--seed", "42",
+            "--samples-local", "500"]
+    for extra in ([], ["-l", "20", "-f", "1"], ["-d"]):
+        r = subprocess.run(base + extra, cwd=root, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        vec = ast.literal_eval(r.stdout.strip().splitlines()[-1])
+        assert len(vec) == 7 and 0.25 <= vec[0] <= 10.0 and vec[1] > 0
+        assert set(r.stderr.strip()) <= {"."} or "Info" in r.stderr   # progress dots (divergence.jl:140)
+    # exact undirected run equals the API call with the same seed
+    direct = dv.wGCL(edges, ew, comm, emb, np.zeros(115), vw, *EMPTY, False, 42, 500, False)
+    r = subprocess.run(base, cwd=root, capture_output=True, text=True, timeout=300)
+    vec = ast.literal_eval(r.stdout.strip().splitlines()[-1])
+    np.testing.assert_allclose(vec, direct, rtol=1e-12)
+    bad = subprocess.run(base[:3] + ["-g", "/nonexistent"], cwd=root, capture_output=True, text=True)
+    assert bad.returncode == 1 and "Usage" in bad.stdout
