@@ -1,21 +1,17 @@
-# The reference's example/CGE_CLI.jl with one line changed: `using CGEB200` instead of
-# `using CGE`.  Every flag of the reference CLI keeps working (parseargs is CGE.jl's own).
-push!(LOAD_PATH, @__DIR__)
+# Runs the reference's own CLI script on the B200 scorer without copying it: the text of
+# example/CGE_CLI.jl is read from the CGE.jl checkout, its `using CGE` line is dropped and the
+# rest is evaluated after `using .CGEB200`, whose wGCL / wGCL_directed / parseargs / landmarks are
+# then the names the script resolves.  Every flag of the reference CLI keeps working.
+#
+#   julia CGE_CLI_B200.jl -g G.edgelist -c G.ecg -e G.embedding -l 200 --seed 42
+#
+# The script is located through ENV["CGE_REFERENCE_CLI"] or pathof(CGE).
 include(joinpath(@__DIR__, "CGEB200.jl"))
 using .CGEB200
+import CGE
 
-edges, weights, vweights, comm, clusters, embed, verbose, land, forced, method, directed, split, seed, samples = parseargs()
-distances = zeros(length(vweights))
-init_edges = Array{Int,2}(undef, 0, 0)
-init_vweights = Vector{Float64}()
-init_eweights = Vector{Float64}()
-init_embed = Array{Float64,2}(undef, 0, 0)
-v_to_l = Int[]
-if land != -1
-    init_edges, init_vweights, init_eweights, init_embed = copy(edges), copy(vweights), copy(weights), copy(embed)
-    distances, embed, comm, edges, weights, vweights, v_to_l = landmarks(edges, weights, vweights,
-        clusters, comm, embed, verbose, land, forced, method, directed)
-end
-score = directed ? wGCL_directed : wGCL
-println(score(edges, weights, comm, embed, distances, vweights, init_vweights, v_to_l, init_edges,
-              init_eweights, init_embed, split, seed, samples, verbose))
+cli = get(ENV, "CGE_REFERENCE_CLI",
+          normpath(joinpath(dirname(pathof(CGE)), "..", "example", "CGE_CLI.jl")))
+isfile(cli) || error("reference CLI script not found: $cli (set CGE_REFERENCE_CLI)")
+body = replace(read(cli, String), r"^\s*using\s+CGE\s*$"m => "")
+include_string(Main, body, cli)
