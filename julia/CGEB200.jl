@@ -16,7 +16,7 @@
 # cge_jl_b200/divergence.py, which IS exercised by the test-suite through the same C ABI.
 module CGEB200
 
-using CGE
+using CGE: parseargs, landmarks, louvain_clust   # re-exported unchanged; wGCL* are defined here
 using StatsBase
 using Random
 
