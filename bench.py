@@ -154,7 +154,8 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": w["data"], "config": {"workload": w["name"], "sample": sample},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(),
+                         "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -324,7 +325,9 @@ def run_b200(args):
     if world == 1 and not args.no_cpu_baseline:
         v, dt, a, sw, note = oracle_sample(w, args.ref_alphas)
         line["cpu_baseline"] = {
-            "value": v, "unit": UNIT, "cores": 1, "kind": "port",
+            "value": v, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": "port",
+            "threads_note": "the reference has no threading (no @threads/@spawn/Distributed in "
+                            "src/): JULIA_NUM_THREADS does not change it, so one core is used",
             "sample": f"oracle/ C port of wGCL, first {a} of 40 alpha values ({sw} fixed-point "
                       f"passes) of the same workload, {dt:.1f} s; {note}"}
     print(json.dumps(line))
