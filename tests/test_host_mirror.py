@@ -137,3 +137,37 @@ def test_draw_samples_dense_and_complete_graphs():
     k5 = np.array([[i, j] for i in range(1, 6) for j in range(i + 1, 6) if (i, j) != (2, 4)])
     _, _, _, ni, nj = draw_samples(k5, np.ones(len(k5)), 5, 20, 42, False, True)
     assert np.all(ni == 2) and np.all(nj == 4)
+
+
+def _bf16_rn(x32):
+    """Round-to-nearest-even float32 -> bfloat16 (kept in float32), as __float2bfloat16_rn."""
+    b = x32.astype(np.float32).view(np.uint32).astype(np.uint64)
+    b = (b + 0x7FFF + ((b >> 16) & 1)) & 0xFFFF0000
+    return b.astype(np.uint32).view(np.float32)
+
+
+def test_diameter_filter_error_bound():
+    """The tensor-core diameter filter (cge_diameter.cu) keeps every tile whose approximate maximum
+    is within 2E of the global one, E = 1e-3 * max_i |x_i|^2.  Emulate its arithmetic (BF16 hi/lo
+    split, three-term Gram entry, FP32 norms) and check that the real error stays an order of
+    magnitude below E for centred data of several shapes and scales."""
+    rng = np.random.default_rng(0)
+    for n, d, scale in ((400, 128, 1.0), (300, 32, 1e3), (300, 7, 1e-3), (200, 64, 37.0)):
+        x = rng.normal(size=(n, d)) * scale
+        x[:5] *= 3.0                       # a few far points decide the diameter
+        x = x - x.mean(0)
+        hi = _bf16_rn(x.astype(np.float32))
+        lo = _bf16_rn((x - hi.astype(np.float64)).astype(np.float32))
+        assert np.abs(x - hi - lo).max() <= 2.0 ** -16 * np.abs(x).max()
+        h64, l64 = hi.astype(np.float64), lo.astype(np.float64)
+        gram = (h64 @ h64.T + h64 @ l64.T + l64 @ h64.T).astype(np.float32)   # FP32 accumulator
+        nf = (x * x).sum(1).astype(np.float32)
+        approx = (nf[:, None] + nf[None, :] - 2.0 * gram).astype(np.float64)
+        exact = ((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+        rmax2 = (x * x).sum(1).max()
+        err = np.abs(approx - exact).max()
+        assert err <= 1e-4 * rmax2, (n, d, scale, err / rmax2)
+        # hence the candidate rule cannot lose the true argmax
+        E = 1e-3 * rmax2
+        i, j = np.unravel_index(np.argmax(exact), exact.shape)
+        assert approx[i, j] >= approx.max() - 2 * E
