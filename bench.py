@@ -322,6 +322,21 @@ def run_b200(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"
                                     if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
     }
+    if int(stats.regime) == 2:
+        # recompute regime: FP64-pipe roofline, algorithmic work (2d + 6) flop per pair and pass
+        # (SURVEY.md 8(d)); peak = FP64 FMA throughput measured on this device by the library
+        d_emb = w["emb"].shape[1]
+        flops = (2.0 * d_emb + 6.0) * pairs / world * passes_per_launch
+        fp64_peak = sc.fp64_peak_tflops()
+        ach = flops / avg_launch_s / 1e12 if avg_launch_s > 0 else 0.0
+        line["roofline"].update({
+            "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+            "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+            "flops_per_launch": flops,
+            "note": "achieved = (2d+6) flop x unordered pairs x passes in the launch / CUDA-event "
+                    "duration; sqrt, divide and the power are counted as 0 flop, so this is a lower "
+                    "bound on executed work",
+            "peak_source": "cge_b200_measure_fp64_peak (DFMA microbenchmark on this device)"})
     if world == 1 and not args.no_cpu_baseline:
         v, dt, a, sw, note = oracle_sample(w, args.ref_alphas)
         line["cpu_baseline"] = {

@@ -67,7 +67,7 @@ EXPORTS = [
     "cge_b200_create", "cge_b200_destroy", "cge_b200_upload", "cge_b200_run",
     "cge_b200_comm_id_size", "cge_b200_comm_unique_id", "cge_b200_comm_init",
     "cge_b200_shard_plan", "cge_b200_debug_read", "cge_b200_p2p_handle_size",
-    "cge_b200_p2p_export", "cge_b200_p2p_import",
+    "cge_b200_p2p_export", "cge_b200_p2p_import", "cge_b200_measure_fp64_peak",
 ]
 
 _lib = None
@@ -103,6 +103,7 @@ def load():
     lib.cge_b200_p2p_handle_size.restype = C.c_int
     lib.cge_b200_p2p_export.argtypes = [vp, C.c_int64, vp]
     lib.cge_b200_p2p_import.argtypes = [vp, vp]
+    lib.cge_b200_measure_fp64_peak.argtypes = [vp, _pd]
     lib.cge_b200_debug_read.argtypes = [vp, C.c_int, _pd, C.c_int64]
     _lib = lib
     return lib

@@ -1653,6 +1653,14 @@ int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles) {
     return 0;
 }
 
+int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops) {
+    if (!h || !tflops) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    *tflops = measure_fp64_peak_tflops(h->sm_count, h->stream);
+    if (*tflops <= 0.0) return fail(CGE_B200_ERR_CUDA, "FP64 peak measurement failed");
+    return 0;
+}
+
 int cge_b200_shard_plan(int64_t n, int rank, int n_ranks, int64_t *n_tiles, int64_t *tile_begin,
                         int64_t *tile_end) {
     if (n <= 0 || n_ranks < 1 || rank < 0 || rank >= n_ranks || !n_tiles || !tile_begin ||

@@ -172,6 +172,11 @@ class Scorer:
         _check(self._lib.cge_b200_run(self._h, _pd(out), C.byref(n_out), C.byref(stats)))
         return out[: n_out.value].copy(), stats
 
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        _check(self._lib.cge_b200_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
     def debug_read(self, what, n):
         size = n * n if what == 0 else n
         buf = np.zeros(size)

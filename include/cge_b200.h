@@ -176,6 +176,10 @@ int cge_b200_p2p_handle_size(void);
 int cge_b200_p2p_export(cge_b200_handle *h, int64_t max_vertices, void *handle_out);
 int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles);
 
+/* Measured FP64 FMA throughput of the handle's device in TFLOP/s (2 flop per FMA): the roofline
+ * denominator of the recompute regime, which MEASURED_PEAKS.json does not provide. */
+int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops);
+
 /* Host-only: the tile range [*tile_begin, *tile_end) of the upper-triangular tile sequence
  * that `rank` of `n_ranks` owns for an n-vertex problem, and the tile count. No GPU needed. */
 int cge_b200_shard_plan(int64_t n, int rank, int n_ranks, int64_t *n_tiles,
