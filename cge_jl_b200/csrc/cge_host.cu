@@ -909,6 +909,95 @@ static int nccl_check(int rc, const char *what) {
                                        (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
 }
 
+// Distance extrema over all ranks (divergence.jl:92): the bit patterns of non-negative doubles
+// order like the values, so an integer min / max does it -- through the in-process group or NCCL.
+static int reduce_extrema_across_ranks(cge_b200_handle *h, unsigned long long *lohi,
+                                       cudaStream_t st) {
+    if (h->n_ranks > 1 && h->group) {
+        LocalGroup &G = *h->group;
+        unsigned long long mine[2];
+        CUDA_TRY(cudaMemcpyAsync(mine, lohi, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        G.lohi[2 * h->rank] = mine[0];
+        G.lohi[2 * h->rank + 1] = mine[1];
+        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        for (int r = 0; r < G.n; ++r) {  // bit patterns of non-negative doubles order like the values
+            mine[0] = std::min(mine[0], G.lohi[2 * r]);
+            mine[1] = std::max(mine[1], G.lohi[2 * r + 1]);
+        }
+        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        CUDA_TRY(cudaMemcpyAsync(lohi, mine, 16, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));  // `mine` is a local
+    } else if (h->n_ranks > 1) {
+        if (int rc = nccl_check(g_nccl.AllReduce(lohi, lohi, 1, kNcclU64, kNcclMin, h->nccl_comm, st),
+                                "ncclAllReduce(min)"))
+            return rc;
+        if (int rc = nccl_check(
+                g_nccl.AllReduce(lohi + 1, lohi + 1, 1, kNcclU64, kNcclMax, h->nccl_comm, st),
+                "ncclAllReduce(max)"))
+            return rc;
+    }
+    return 0;
+}
+
+// Landmark mode: extrema of the ORIGINAL graph's distances (divergence.jl:104-115 / 386-397); only
+// the maximum matters (the minimum is the zero diagonal).  Large graphs go through the tensor-core
+// filter of cge_diameter.cu and an FP64 check of its candidate tiles, the rest (and any case the
+// filter cannot prune) through the all-FP64 pass.  Writes the bit pattern into lohi_full[0..1].
+static int full_graph_extrema(cge_b200_handle *h, cge_b200_stats &S, unsigned long long *lohi_full,
+                              int dp, cudaStream_t st) {
+    const int gridf = (int)std::max<int64_t>(
+        1, std::min<int64_t>(h->n_tiles_full, (int64_t)2 * h->sm_count));
+    bool exact_all = true;
+    S.diam_candidate_tiles = -1;
+    if (h->diam_ok) {
+        // tensor-core filter, then FP64 verification of the candidate tiles only
+        unsigned *ctr = h->diam_ctr.as<unsigned>();  // [0] strip counter [1] gmax [2] rmax [3] count
+        CUDA_TRY(cudaMemsetAsync(ctr, 0, 64, st));
+        launch_pack_bf16(h->emb_full.as<double>(), h->diam_mean.as<double>(), dp,
+                         (int)h->n_full, (int)h->d, (int)h->nbf,
+                         h->diam_packed.as<unsigned char>(), h->diam_norms.as<float>(),
+                         ctr + 2, st);
+        DiamArgs da;
+        da.packed = h->diam_packed.as<unsigned char>();
+        da.norms = h->diam_norms.as<float>();
+        da.nb = (int)h->nbf;
+        da.ksteps = dp / 16;
+        da.strips = h->diam_strips.as<int4>();
+        da.n_strips = h->diam_n_strips;
+        da.strip_counter = ctr;
+        da.tile_max = h->diam_tilemax.as<float>();
+        da.gmax_bits = ctr + 1;
+        CUDA_TRY(launch_diameter_filter(da, std::min(h->diam_n_strips, h->sm_count), st));
+        float rel = 1e-3f;
+        if (const char *e = getenv("CGE_B200_DIAM_REL")) rel = (float)atof(e);
+        const int cap = 1 << 20;
+        launch_select_candidates(da.tile_max, h->n_tiles_full, ctr + 1, ctr + 2, rel,
+                                 h->diam_list.as<int>(), cap, (int *)(ctr + 3), st);
+        h->launches += 3;
+        unsigned hc[4];
+        CUDA_TRY(cudaMemcpyAsync(hc, ctr, 16, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const int64_t cand = (int)hc[3];
+        S.diam_candidate_tiles = (int32_t)cand;
+        if (cand > 0 && cand <= cap && cand * 8 <= h->n_tiles_full) {
+            const int gridc = (int)std::max<int64_t>(1, std::min<int64_t>(cand, 2 * h->sm_count));
+            k_build_dist<false><<<gridc, NTHREADS, 0, st>>>(
+                h->emb_full.as<double>(), dp, nullptr, (int)h->n_full,
+                h->tile_ij_full.as<int2>(), 0, cand, nullptr, lohi_full, h->diam_list.as<int>());
+            ++h->launches;
+            exact_all = false;
+        }
+    }
+    if (exact_all) {
+        k_build_dist<false><<<gridf, NTHREADS, 0, st>>>(
+            h->emb_full.as<double>(), dp, nullptr, (int)h->n_full, h->tile_ij_full.as<int2>(),
+            0, h->n_tiles_full, nullptr, lohi_full);
+        ++h->launches;
+    }
+    return 0;
+}
+
 static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_stats *stats) {
     if (!h->uploaded) return fail(CGE_B200_ERR_STATE, "run() before upload()");
     auto wall0 = std::chrono::steady_clock::now();
@@ -991,30 +1080,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                                                            lohi);
         ++h->launches;
     }
-    if (h->n_ranks > 1 && h->group) {
-        LocalGroup &G = *h->group;
-        unsigned long long mine[2];
-        CUDA_TRY(cudaMemcpyAsync(mine, lohi, 16, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        G.lohi[2 * h->rank] = mine[0];
-        G.lohi[2 * h->rank + 1] = mine[1];
-        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
-        for (int r = 0; r < G.n; ++r) {  // bit patterns of non-negative doubles order like the values
-            mine[0] = std::min(mine[0], G.lohi[2 * r]);
-            mine[1] = std::max(mine[1], G.lohi[2 * r + 1]);
-        }
-        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
-        CUDA_TRY(cudaMemcpyAsync(lohi, mine, 16, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaStreamSynchronize(st));  // `mine` is a local
-    } else if (h->n_ranks > 1) {
-        if (int rc = nccl_check(g_nccl.AllReduce(lohi, lohi, 1, kNcclU64, kNcclMin, h->nccl_comm, st),
-                                "ncclAllReduce(min)"))
-            return rc;
-        if (int rc = nccl_check(
-                g_nccl.AllReduce(lohi + 1, lohi + 1, 1, kNcclU64, kNcclMax, h->nccl_comm, st),
-                "ncclAllReduce(max)"))
-            return rc;
-    }
+    if (h->n_ranks > 1)
+        if (int rc = reduce_extrema_across_ranks(h, lohi, st)) return rc;
     if (local_tiles > 0 && stored) {
         k_transform<<<4 * h->sm_count, 256, 0, st>>>(h->q.as<double>(),
                                                      (size_t)local_tiles * TILE_ELEMS, lohi);
@@ -1025,57 +1092,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     // ---- landmark mode: extrema of the full graph (divergence.jl:104-115 / 386-397) ----
     const long long SK = h->K * h->n_sets;
     if (h->K > 0) {
-        if (h->landmark) {
-            const int gridf = (int)std::max<int64_t>(
-                1, std::min<int64_t>(h->n_tiles_full, (int64_t)2 * h->sm_count));
-            bool exact_all = true;
-            S.diam_candidate_tiles = -1;
-            if (h->diam_ok) {
-                // tensor-core filter, then FP64 verification of the candidate tiles only
-                unsigned *ctr = h->diam_ctr.as<unsigned>();  // [0] strip counter [1] gmax [2] rmax [3] count
-                CUDA_TRY(cudaMemsetAsync(ctr, 0, 64, st));
-                launch_pack_bf16(h->emb_full.as<double>(), h->diam_mean.as<double>(), dp,
-                                 (int)h->n_full, (int)h->d, (int)h->nbf,
-                                 h->diam_packed.as<unsigned char>(), h->diam_norms.as<float>(),
-                                 ctr + 2, st);
-                DiamArgs da;
-                da.packed = h->diam_packed.as<unsigned char>();
-                da.norms = h->diam_norms.as<float>();
-                da.nb = (int)h->nbf;
-                da.ksteps = dp / 16;
-                da.strips = h->diam_strips.as<int4>();
-                da.n_strips = h->diam_n_strips;
-                da.strip_counter = ctr;
-                da.tile_max = h->diam_tilemax.as<float>();
-                da.gmax_bits = ctr + 1;
-                CUDA_TRY(launch_diameter_filter(da, std::min(h->diam_n_strips, h->sm_count), st));
-                float rel = 1e-3f;
-                if (const char *e = getenv("CGE_B200_DIAM_REL")) rel = (float)atof(e);
-                const int cap = 1 << 20;
-                launch_select_candidates(da.tile_max, h->n_tiles_full, ctr + 1, ctr + 2, rel,
-                                         h->diam_list.as<int>(), cap, (int *)(ctr + 3), st);
-                h->launches += 3;
-                unsigned hc[4];
-                CUDA_TRY(cudaMemcpyAsync(hc, ctr, 16, cudaMemcpyDeviceToHost, st));
-                CUDA_TRY(cudaStreamSynchronize(st));
-                const int64_t cand = (int)hc[3];
-                S.diam_candidate_tiles = (int32_t)cand;
-                if (cand > 0 && cand <= cap && cand * 8 <= h->n_tiles_full) {
-                    const int gridc = (int)std::max<int64_t>(1, std::min<int64_t>(cand, 2 * h->sm_count));
-                    k_build_dist<false><<<gridc, NTHREADS, 0, st>>>(
-                        h->emb_full.as<double>(), dp, nullptr, (int)h->n_full,
-                        h->tile_ij_full.as<int2>(), 0, cand, nullptr, lohi + 2, h->diam_list.as<int>());
-                    ++h->launches;
-                    exact_all = false;
-                }
-            }
-            if (exact_all) {
-                k_build_dist<false><<<gridf, NTHREADS, 0, st>>>(
-                    h->emb_full.as<double>(), dp, nullptr, (int)h->n_full, h->tile_ij_full.as<int2>(),
-                    0, h->n_tiles_full, nullptr, lohi + 2);
-                ++h->launches;
-            }
-        }
+        if (h->landmark)
+            if (int rc = full_graph_extrema(h, S, lohi + 2, dp, st)) return rc;  // lohi[2..3]
         const double *e = h->landmark ? h->emb_full.as<double>() : h->emb.as<double>();
         const double *dg = h->landmark ? nullptr : h->dist.as<double>();
         const unsigned long long *lh = h->landmark ? lohi + 2 : lohi;
