@@ -1209,8 +1209,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                              : small ? fp_kernel_rt(h->directed)
                                      : fp_kernel(m, h->directed);
             const int threads = ring ? fp_ring_threads() : NTHREADS;
-            const size_t smem = ring ? fp_ring_smem_bytes(h->directed) : 0;
-            if (ring)
+            const size_t smem = ring ? fp_ring_smem_bytes(h->directed) : (!stored ? rc_smem_bytes() : 0);
+            if (smem > 0)
                 CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)smem));
             int bps = 0;
@@ -1676,6 +1676,26 @@ int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops) {
     CUDA_TRY(cudaSetDevice(h->device));
     *tflops = measure_fp64_peak_tflops(h->sm_count, h->stream);
     if (*tflops <= 0.0) return fail(CGE_B200_ERR_CUDA, "FP64 peak measurement failed");
+    return 0;
+}
+
+int cge_b200_selftest_math(cge_b200_handle *h, int64_t n_samples, uint64_t seed,
+                           int64_t *sqrt_mismatches, int64_t *div_mismatches) {
+    if (!h || n_samples <= 0 || !sqrt_mismatches || !div_mismatches)
+        return fail(CGE_B200_ERR_ARG, "bad selftest_math argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    unsigned long long *dev = nullptr, host[2] = {0, 0};
+    CUDA_TRY(cudaMalloc(&dev, 16));
+    cudaError_t e = cudaMemsetAsync(dev, 0, 16, h->stream);
+    if (e == cudaSuccess) {
+        launch_selftest_math(n_samples, seed, dev, 8 * h->sm_count, h->stream);
+        e = cudaMemcpyAsync(host, dev, 16, cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev);
+    CUDA_TRY(e);
+    *sqrt_mismatches = (int64_t)host[0];
+    *div_mismatches = (int64_t)host[1];
     return 0;
 }
 

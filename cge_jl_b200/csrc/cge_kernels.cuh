@@ -724,6 +724,9 @@ void launch_select_candidates(const float *tile_max, long long n_tiles, const un
 // recompute regime (cge_recompute.cu): kind as in launch_tiles, exponent taken from a.m
 void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 const void *fp_kernel_rc(int directed);
+size_t rc_smem_bytes();  // dynamic shared memory of every recompute kernel
+void launch_selftest_math(long long n, unsigned long long seed, unsigned long long *out, int grid,
+                          cudaStream_t st);
 double measure_fp64_peak_tflops(int sm_count, cudaStream_t st);
 int fp_ring_threads();
 void launch_tiles_part0(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);

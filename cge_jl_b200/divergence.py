@@ -177,6 +177,14 @@ class Scorer:
         _check(self._lib.cge_b200_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
 
+    def selftest_math(self, n_samples, seed=1):
+        """(sqrt mismatches, divide mismatches) of the recompute epilogue's branch-free forms
+        against the IEEE operations on ``n_samples`` pseudo-random operands."""
+        a, b = C.c_int64(), C.c_int64()
+        _check(self._lib.cge_b200_selftest_math(self._h, int(n_samples), int(seed), C.byref(a),
+                                                C.byref(b)))
+        return a.value, b.value
+
     def debug_read(self, what, n):
         size = n * n if what == 0 else n
         buf = np.zeros(size)

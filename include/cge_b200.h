@@ -180,6 +180,14 @@ int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles);
  * denominator of the recompute regime, which MEASURED_PEAKS.json does not provide. */
 int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops);
 
+/* Self-test of the recompute regime's arithmetic: its epilogue evaluates sqrt and divide with
+ * branch-free instruction sequences (so that 8 pairs interleave in the FP64 pipe) that must return
+ * the bits of the IEEE operations the stored regime and the reference use (Julia sqrt and /,
+ * divergence.jl:92, auxilary.jl:19).  Runs n_samples pseudo-random operands in the epilogue's
+ * ranges through both and counts the results that differ. */
+int cge_b200_selftest_math(cge_b200_handle *h, int64_t n_samples, uint64_t seed,
+                           int64_t *sqrt_mismatches, int64_t *div_mismatches);
+
 /* Host-only: the tile range [*tile_begin, *tile_end) of the upper-triangular tile sequence
  * that `rank` of `n_ranks` owns for an n-vertex problem, and the tile count. No GPU needed. */
 int cge_b200_shard_plan(int64_t n, int rank, int n_ranks, int64_t *n_tiles,

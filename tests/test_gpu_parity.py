@@ -156,6 +156,12 @@ def test_recompute_regime(scorer, directed, n, k, d, driver):
     assert_parity(out, stats, ref, tr)
 
 
+def test_recompute_branch_free_math_matches_ieee(scorer):
+    """The recompute epilogue's branch-free sqrt / divide return the bits of the IEEE operations
+    (2^26 pseudo-random operands in the epilogue's ranges, zeros and denormals included)."""
+    assert scorer.selftest_math(1 << 26, seed=2024) == (0, 0)
+
+
 def test_recompute_regime_landmarks_with_diagonal(scorer):
     """Landmark mode has a non-zero diagonal (d_ii) and lo > 0 possible: recompute vs stored."""
     edges, ew, vw, comm, emb = load_fixture("test115.npz")

@@ -49,10 +49,14 @@ def test_20k_properties_and_driver_agreement(scorer, directed):
     np.testing.assert_allclose(out1, out, rtol=1e-12, atol=1e-15)
 
 
-@pytest.mark.parametrize("directed", [False, True])
-def test_stored_and_recompute_regimes_agree(scorer, directed):
+@pytest.mark.parametrize("directed,d", [(False, 40), (True, 40), (False, 12), (True, 24)])
+def test_stored_and_recompute_regimes_agree(scorer, directed, d):
+    """300 tiles: every CTA walks 2-3 tiles, so the recompute kernel's cross-tile staging (the
+    next tile's first chunk requested during the last chunk of the current one) runs with 1, 2
+    and 3 chunks per tile.  Two vertices share an embedding row (distance exactly 0)."""
     n = 3001
-    data = planted_partition(n, k=9, d=40, seed=77, directed=directed, weighted=True)
+    data = planted_partition(n, k=9, d=d, seed=77, directed=directed, weighted=True)
+    data[4][1234] = data[4][77]
     samples = dv.draw_samples(data[0], data[1], n, 3000, 42, directed, True)
     a, sa = _run(scorer, directed, data, samples, 2, 1, n)
     b, sb = _run(scorer, directed, data, samples, 2, 2, n)
