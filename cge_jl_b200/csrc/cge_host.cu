@@ -1679,6 +1679,77 @@ int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops) {
     return 0;
 }
 
+int cge_b200_sample_non_edges(cge_b200_handle *h, int64_t n, int64_t m, const int64_t *edge_src,
+                              const int64_t *edge_dst, int32_t index_base, int32_t directed,
+                              int64_t n_samples, int64_t n_sets, uint64_t seed, int64_t *out_i,
+                              int64_t *out_j, double *draws_per_sample) {
+    if (!h || n < 2 || n >= ((int64_t)1 << 31) || m < 0 || (m > 0 && (!edge_src || !edge_dst)) ||
+        (index_base != 0 && index_base != 1) || n_samples <= 0 || n_sets <= 0 || !out_i || !out_j)
+        return fail(CGE_B200_ERR_ARG, "bad sample_non_edges argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t total = n_samples * n_sets;
+    uint64_t slots = 1024;
+    while (slots < 2 * (uint64_t)m) slots <<= 1;  // load factor <= 0.5
+    DevBuf src, dst, table, counts, oi, oj;
+    auto release = [&]() {
+        for (DevBuf *b : {&src, &dst, &table, &counts, &oi, &oj}) b->release();
+    };
+    int rc = 0;
+    if (!rc) rc = src.ensure((size_t)std::max<int64_t>(m, 1) * 8);
+    if (!rc) rc = dst.ensure((size_t)std::max<int64_t>(m, 1) * 8);
+    if (!rc) rc = table.ensure((size_t)slots * 8);
+    if (!rc) rc = counts.ensure(32);
+    if (!rc) rc = oi.ensure((size_t)total * 8);
+    if (!rc) rc = oj.ensure((size_t)total * 8);
+    unsigned long long hc[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) {
+        if (e == cudaSuccess) e = r;
+    };
+    if (!rc) {
+        if (m > 0) {
+            step(cudaMemcpyAsync(src.p, edge_src, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+            step(cudaMemcpyAsync(dst.p, edge_dst, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        }
+        step(cudaMemsetAsync(table.p, 0xFF, (size_t)slots * 8, st));
+        step(cudaMemsetAsync(counts.p, 0, 32, st));
+        if (m > 0 && e == cudaSuccess)
+            launch_edge_set_insert(src.as<long long>(), dst.as<long long>(), m, n, index_base,
+                                   directed, table.as<unsigned long long>(), slots - 1,
+                                   counts.as<unsigned long long>(), 4 * h->sm_count, st);
+        step(cudaMemcpyAsync(hc, counts.p, 32, cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
+        step(cudaGetLastError());
+    }
+    const uint64_t candidates = directed ? (uint64_t)n * (uint64_t)(n - 1)
+                                         : (uint64_t)n * (uint64_t)(n - 1) / 2;
+    if (!rc && e == cudaSuccess) {
+        if (hc[1] > 0)
+            rc = fail(CGE_B200_ERR_ARG, std::to_string(hc[1]) + " edges with an endpoint outside 1..n");
+        else if (hc[0] >= candidates)  // sample() of an empty collection (divergence.jl:137 leaves NE empty)
+            rc = fail(CGE_B200_ERR_ARG, "collection must be non-empty: the graph has no non-edges");
+    }
+    if (!rc && e == cudaSuccess) {
+        launch_sample_non_edges(n, directed, index_base, table.as<unsigned long long>(), slots - 1,
+                                seed, total, oi.as<long long>(), oj.as<long long>(),
+                                counts.as<unsigned long long>(), 4 * h->sm_count, st);
+        step(cudaMemcpyAsync(out_i, oi.p, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(out_j, oj.p, (size_t)total * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(hc, counts.p, 32, cudaMemcpyDeviceToHost, st));
+        step(cudaStreamSynchronize(st));
+        step(cudaGetLastError());
+        if (e == cudaSuccess && hc[2] > 0)
+            rc = fail(CGE_B200_ERR_STATE, std::to_string(hc[2]) +
+                                              " samples found no non-edge in 2^22 draws each");
+        if (draws_per_sample) *draws_per_sample = (double)hc[3] / (double)total;
+    }
+    release();
+    if (rc) return rc;
+    CUDA_TRY(e);
+    return 0;
+}
+
 int cge_b200_selftest_math(cge_b200_handle *h, int64_t n_samples, uint64_t seed,
                            int64_t *sqrt_mismatches, int64_t *div_mismatches) {
     if (!h || n_samples <= 0 || !sqrt_mismatches || !div_mismatches)

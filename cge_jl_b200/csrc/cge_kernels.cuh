@@ -728,6 +728,16 @@ size_t rc_smem_bytes();  // dynamic shared memory of every recompute kernel
 void launch_selftest_math(long long n, unsigned long long seed, unsigned long long *out, int grid,
                           cudaStream_t st);
 double measure_fp64_peak_tflops(int sm_count, cudaStream_t st);
+// device sampler of non-edges (cge_sampler.cu)
+void launch_edge_set_insert(const long long *src, const long long *dst, long long m, long long n,
+                            int index_base, int directed, unsigned long long *table,
+                            unsigned long long mask, unsigned long long *counts, int grid,
+                            cudaStream_t st);
+void launch_sample_non_edges(long long n, int directed, int index_base,
+                             const unsigned long long *table, unsigned long long mask,
+                             unsigned long long seed, long long total, long long *out_i,
+                             long long *out_j, unsigned long long *counts, int grid,
+                             cudaStream_t st);
 int fp_ring_threads();
 void launch_tiles_part0(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);
 void launch_tiles_part1(int m, int kind, int grid, cudaStream_t stream, const SweepArgs &a);

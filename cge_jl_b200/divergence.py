@@ -87,7 +87,12 @@ def _sample_non_edges(rng, n, codes, K, directed):
     return out_i, out_j
 
 
-def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact):
+# above this many vertices the Julia wrapper (julia/CGEB200.jl) stops materialising NE; the device
+# sampler takes over when a Scorer is passed to draw_samples
+NE_MATERIALIZE_LIMIT = 30_000
+
+
+def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact, device=None):
     """Draw the positive / negative pairs of the local score where the reference draws them.
 
     Returns ``(pos_i, pos_j, pos_w, neg_i, neg_j)`` with shape ``(n_sets, K)``, 1-based ids of
@@ -97,6 +102,10 @@ def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact):
     continuation draw while the weights stay those of the first (the overwrite at
     divergence.jl:505-510).  NumPy's generator replaces Julia's RNG stream: the sets are
     identically distributed, not identical.
+
+    ``device``: a :class:`Scorer`; the negative pairs then come from
+    ``cge_b200_sample_non_edges`` (edge hash set + rejection draws on the GPU) instead of the NumPy
+    rejection sampler -- what a host uses once NE no longer fits (``NE_MATERIALIZE_LIMIT``).
     """
     adj_edges = _i64(adj_edges)
     w = _f64(adj_eweights)
@@ -113,6 +122,9 @@ def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact):
     nj = np.empty_like(pi)
     pw = np.empty((n_sets, K))
     free_rng = np.random.default_rng()
+    if device is not None:
+        dev_seed = int(seed) if seed != -1 else int(free_rng.integers(0, 2**63))
+        ni, nj = device.sample_non_edges(adj_edges, adj_n, K, n_sets, dev_seed, directed)
     for s in range(n_sets):
         rng = np.random.default_rng(seed) if seed != -1 else free_rng
         idx = rng.integers(0, m, size=K)
@@ -120,8 +132,9 @@ def draw_samples(adj_edges, adj_eweights, adj_n, K, seed, directed, exact):
         if directed and exact:
             idx = rng.integers(0, m, size=K)  # second draw, no reseed (divergence.jl:510)
         pi[s], pj[s] = e_i[idx], e_j[idx]
-        rng = np.random.default_rng(seed) if seed != -1 else free_rng
-        ni[s], nj[s] = _sample_non_edges(rng, adj_n, codes, K, directed)
+        if device is None:
+            rng = np.random.default_rng(seed) if seed != -1 else free_rng
+            ni[s], nj[s] = _sample_non_edges(rng, adj_n, codes, K, directed)
     return pi, pj, pw, ni, nj
 
 
@@ -176,6 +189,21 @@ class Scorer:
         v = C.c_double()
         _check(self._lib.cge_b200_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+    def sample_non_edges(self, edges, n, K, n_sets=1, seed=0, directed=False, index_base=1,
+                         return_draws=False):
+        """``cge_b200_sample_non_edges``: ``(neg_i, neg_j)`` of shape ``(n_sets, K)``, uniform over
+        the non-edges of the ``n``-vertex graph with replacement."""
+        edges = _i64(edges).reshape(-1, 2)
+        src, dst = _i64(edges[:, 0]), _i64(edges[:, 1])
+        oi = np.empty((int(n_sets), int(K)), dtype=np.int64)
+        oj = np.empty_like(oi)
+        draws = C.c_double()
+        _check(self._lib.cge_b200_sample_non_edges(
+            self._h, int(n), int(edges.shape[0]), _pi(src), _pi(dst), int(index_base),
+            int(bool(directed)), int(K), int(n_sets), int(seed) & (2**64 - 1), _pi(oi), _pi(oj),
+            C.byref(draws)))
+        return (oi, oj, draws.value) if return_draws else (oi, oj)
 
     def selftest_math(self, n_samples, seed=1):
         """(sqrt mismatches, divide mismatches) of the recompute epilogue's branch-free forms
@@ -286,20 +314,22 @@ def _score(directed, edges, eweights, comm, embed, distances, vweights, init_vwe
         print(f"Embedding has {np.asarray(embed).shape[1]} dimensions")
     if len(distances) != no_vertices:                   # divergence.jl:81
         raise AssertionError(_ASSERTS[_lib.ERR_ASSERT_DIST])
-    if samples is None and auc_samples > 0:
-        adj_edges = init_edges if landmarks else edges  # divergence.jl:95-102
-        adj_w = init_eweights if landmarks else eweights
-        adj_n = len(init_vweights) if landmarks else no_vertices
-        samples = draw_samples(adj_edges, adj_w, adj_n, int(auc_samples), int(seed), directed,
-                               exact=not landmarks)
-    problem, keep = make_problem(edges, eweights, comm, embed, distances, vweights,
-                                 init_vweights if landmarks else None,
-                                 v_to_l if landmarks else None,
-                                 init_embed if landmarks else None, split, directed, samples,
-                                 max_alphas, driver, regime)
     own = scorer is None
     sc = Scorer() if own else scorer
     try:
+        if samples is None and auc_samples > 0:
+            adj_edges = init_edges if landmarks else edges  # divergence.jl:95-102
+            adj_w = init_eweights if landmarks else eweights
+            adj_n = len(init_vweights) if landmarks else no_vertices
+            # NE (n^2/2 tuples, divergence.jl:121-137) stops fitting: negatives drawn on the device
+            samples = draw_samples(adj_edges, adj_w, adj_n, int(auc_samples), int(seed), directed,
+                                   exact=not landmarks,
+                                   device=sc if adj_n > NE_MATERIALIZE_LIMIT else None)
+        problem, keep = make_problem(edges, eweights, comm, embed, distances, vweights,
+                                     init_vweights if landmarks else None,
+                                     v_to_l if landmarks else None,
+                                     init_embed if landmarks else None, split, directed, samples,
+                                     max_alphas, driver, regime)
         sc.upload(problem, keep)
         out, stats = sc.run()
     finally:

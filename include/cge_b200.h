@@ -180,6 +180,21 @@ int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles);
  * denominator of the recompute regime, which MEASURED_PEAKS.json does not provide. */
 int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops);
 
+/* SURVEY.md 8(f) F1 -- the negative pairs of the local score drawn on the device.  Replaces the
+ * reference's NE construction (all pairs minus the edge Set, divergence.jl:121-137 / 405-421: n^2/2
+ * tuples, infeasible above a few 10^4 vertices) and its sample(NE, auc_samples, replace=true)
+ * (:193-194, 209 / 495-496, 513): the edges go into a hash set in HBM and every sample is an
+ * independent uniform draw from the non-edges (i < j when undirected, ordered pairs i != j when
+ * directed), n_sets x n_samples of them, set-major, ids index_base-based like the edges.
+ * Deterministic in (seed, n, edges); a counter-based generator replaces Julia's stream, so the
+ * sets are identically distributed, not identical -- hosts keep drawing with Julia wherever NE
+ * fits.  A graph without non-edges fails like sample() on an empty collection.
+ * draws_per_sample (may be NULL) returns the mean number of candidate pairs drawn per sample. */
+int cge_b200_sample_non_edges(cge_b200_handle *h, int64_t n, int64_t m, const int64_t *edge_src,
+                              const int64_t *edge_dst, int32_t index_base, int32_t directed,
+                              int64_t n_samples, int64_t n_sets, uint64_t seed, int64_t *out_i,
+                              int64_t *out_j, double *draws_per_sample);
+
 /* Self-test of the recompute regime's arithmetic: its epilogue evaluates sqrt and divide with
  * branch-free instruction sequences (so that 8 pairs interleave in the FP64 pipe) that must return
  * the bits of the IEEE operations the stored regime and the reference use (Julia sqrt and /,

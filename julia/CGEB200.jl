@@ -26,7 +26,7 @@ const LIB = get(ENV, "CGE_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "cge_jl_b200", "libcge_b200.so")))
 const N_ALPHA = 40
 # above this many vertices NE (n^2/2 tuples + two Sets, divergence.jl:121-137) no longer fits in
-# host memory; non-edges are then drawn by rejection (same distribution, different RNG stream)
+# host memory; non-edges are then drawn on the device (same distribution, different RNG stream)
 const NE_MATERIALIZE_LIMIT = 30_000
 
 # mirrors `cge_b200_problem` (include/cge_b200.h)
@@ -67,20 +67,29 @@ function check(rc::Integer)
     throw(ErrorException("libcge_b200 error $rc: $(last_error())"))
 end
 
-# uniform draw from NE without materialising it (used only above NE_MATERIALIZE_LIMIT)
-function sample_non_edges(n::Int, edgeset::Set{Tuple{Int,Int}}, K::Int, directed::Bool)
-    out = Vector{Tuple{Int,Int}}(undef, K)
-    k = 0
-    while k < K
-        i, j = rand(1:n), rand(1:n)
-        i == j && continue
-        if !directed && i > j
-            i, j = j, i
+# uniform draws from NE without materialising it (used only above NE_MATERIALIZE_LIMIT): the
+# device sampler of SURVEY.md 8(f) F1 -- edge hash set in HBM + independent rejection draws,
+# cge_b200_sample_non_edges.  Returns K x n_sets matrices of 1-based ids.
+function sample_non_edges_device(adj_edges::Array{Int,2}, n::Int, K::Int, n_sets::Int, seed::Int,
+                                 directed::Bool)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cge_b200_create, LIB), Cint, (Cint, Ptr{Ptr{Cvoid}}), 0, h))
+    neg_i = Matrix{Int64}(undef, K, n_sets); neg_j = similar(neg_i)
+    m = size(adj_edges, 1)
+    try
+        GC.@preserve adj_edges neg_i neg_j begin
+            src = pointer(adj_edges)                 # column 1 of the column-major m x 2 matrix
+            dst = src + m * sizeof(Int64)            # column 2
+            check(ccall((:cge_b200_sample_non_edges, LIB), Cint,
+                        (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Int32, Int64, Int64,
+                         UInt64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                        h[], n, m, src, dst, 1, directed ? 1 : 0, K, n_sets,
+                        seed == -1 ? rand(UInt64) : UInt64(seed), neg_i, neg_j, C_NULL))
         end
-        (i, j) in edgeset && continue
-        out[k += 1] = (i, j)
+    finally
+        ccall((:cge_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
     end
-    return out
+    return neg_i, neg_j
 end
 
 """
@@ -95,9 +104,9 @@ function draw_samples(adj_edges::Array{Int,2}, adj_eweights::Vector{Float64}, ad
         push!(E, directed ? (e[1], e[2], adj_eweights[i]) :
                             (minimum(e), maximum(e), adj_eweights[i]))      # divergence.jl:131-134 / 415-418
     end
-    edgeset = Set([e[1:2] for e in E])
     NE = nothing
     if adj_n <= NE_MATERIALIZE_LIMIT                                        # divergence.jl:121-137 / 405-421
+        edgeset = Set([e[1:2] for e in E])
         NE = Tuple{Int64,Int64}[]
         for i in 1:adj_n, j in (directed ? 1 : i):adj_n
             i != j && push!(NE, (i, j))
@@ -108,15 +117,18 @@ function draw_samples(adj_edges::Array{Int,2}, adj_eweights::Vector{Float64}, ad
     pos_i = Matrix{Int64}(undef, K, n_sets); pos_j = similar(pos_i)
     neg_i = similar(pos_i); neg_j = similar(pos_i)
     pos_w = Matrix{Float64}(undef, K, n_sets)
+    if NE === nothing
+        neg_i, neg_j = sample_non_edges_device(adj_edges, adj_n, K, n_sets, seed, directed)
+    end
     for s in 1:n_sets
         seed != -1 && Random.seed!(seed)                                    # :184 / :202 / :484 / :504
         first = sample(E, K, replace=true)
         pos_w[:, s] = [e[3] for e in first]
         pairs = (directed && exact) ? sample(E, K, replace=true) : first   # overwrite at :510
         pos_i[:, s] = [e[1] for e in pairs]; pos_j[:, s] = [e[2] for e in pairs]
+        NE === nothing && continue
         seed != -1 && Random.seed!(seed)                                    # :193 / :209 / :494 / :512
-        neg = NE === nothing ? sample_non_edges(adj_n, edgeset, K, directed) :
-                               sample(NE, K, replace=true)
+        neg = sample(NE, K, replace=true)
         neg_i[:, s] = [e[1] for e in neg]; neg_j[:, s] = [e[2] for e in neg]
     end
     return pos_i, pos_j, pos_w, neg_i, neg_j
