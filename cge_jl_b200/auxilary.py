@@ -8,6 +8,7 @@ and the same error behaviour (usage text + exit status 1), following
 """
 from __future__ import annotations
 
+import os
 import sys
 
 import numpy as np
@@ -37,10 +38,34 @@ _USAGE = (
 )
 
 
-def _readdlm(path, dtype, skiprows=0):
-    """Whitespace-delimited numeric table; raises on ragged rows (like a typed ``readdlm``)."""
-    arr = np.loadtxt(path, dtype=dtype, skiprows=skiprows, ndmin=2)
+def readdlm(path, dtype=np.float64, skiprows=0, order="C", n_threads=0):
+    """Whitespace-delimited numeric table, the typed ``readdlm(fn, Float64 | Int)`` of
+    ``auxilary.jl:86,123,150-155``, parsed by the native multi-threaded reader of libcge_b200.so
+    (``cge_b200_table_dims`` + ``cge_b200_read_table``).  Raises ``ValueError``
+    on ragged rows and on cells that are not numbers, like the reference's call does; ``order="F"``
+    returns Julia's column-major layout."""
+    import ctypes as C
+
+    from . import _lib
+
+    lib = _lib.load()
+    rows, cols = C.c_int64(), C.c_int64()
+    fn = os.fsencode(path)
+    if lib.cge_b200_table_dims(fn, int(skiprows), int(n_threads), C.byref(rows), C.byref(cols)) != 0:
+        raise ValueError(_lib.last_error())
+    arr = np.empty((rows.value, cols.value), dtype=np.float64, order=order)
+    rs, cs = (s // 8 for s in arr.strides) if arr.size else (cols.value, 1)
+    if lib.cge_b200_read_table(fn, int(skiprows), int(n_threads), rows.value, cols.value, rs, cs,
+                               arr.ctypes.data_as(C.POINTER(C.c_double))) != 0:
+        raise ValueError(_lib.last_error())
+    if np.issubdtype(np.dtype(dtype), np.integer):
+        if not np.all(arr == np.round(arr)):
+            raise ValueError(f"InexactError: {path} holds non-integer values")
+        return arr.astype(dtype)
     return arr
+
+
+_readdlm = readdlm
 
 
 def _find(argv, flag):
@@ -66,8 +91,6 @@ def _parse(argv):
     i = _find(argv, "-g")
     assert i is not None, "Edgelist file is required"
     fn_edges = argv[i + 1]
-    import os
-
     assert os.path.isfile(fn_edges), f"{fn_edges} is not a file"
     raw = _readdlm(fn_edges, np.float64)
     rows, no_cols = raw.shape

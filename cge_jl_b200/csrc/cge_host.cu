@@ -34,6 +34,7 @@ static int fail(int code, const std::string &msg) {
     g_err = msg;
     return code;
 }
+void set_last_error(const std::string &msg) { g_err = msg; }  // for cge_ingest.cpp
 
 #define CUDA_TRY(expr)                                                                     \
     do {                                                                                   \

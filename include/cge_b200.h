@@ -195,6 +195,19 @@ int cge_b200_sample_non_edges(cge_b200_handle *h, int64_t n, int64_t m, const in
                               int64_t n_samples, int64_t n_sets, uint64_t seed, int64_t *out_i,
                               int64_t *out_j, double *draws_per_sample);
 
+/* SURVEY.md 8(f) F3 -- ingest of the whitespace-delimited numeric tables the reference reads with
+ * readdlm(fn, Float64 | Int) (auxilary.jl:86 edgelist, :123 communities, :150-155 embedding), parsed
+ * on all host cores straight into the caller's matrix.  Host-only, no GPU needed.
+ *   table_dims: rows = non-blank lines after skip_rows lines, cols = cells of the first row.
+ *   read_table: fills out[r*row_stride + c*col_stride] (elements) for a rows x cols table; fails
+ *   with CGE_B200_ERR_ARG when a row has another column count or a cell is not a number in full --
+ *   the failure the reference uses to detect a node2vec header line (retry with skip_rows = 1).
+ * n_threads = 0 uses every hardware thread. */
+int cge_b200_table_dims(const char *path, int64_t skip_rows, int32_t n_threads, int64_t *rows,
+                        int64_t *cols);
+int cge_b200_read_table(const char *path, int64_t skip_rows, int32_t n_threads, int64_t rows,
+                        int64_t cols, int64_t row_stride, int64_t col_stride, double *out);
+
 /* Self-test of the recompute regime's arithmetic: its epilogue evaluates sqrt and divide with
  * branch-free instruction sequences (so that 8 pairs interleave in the FP64 pipe) that must return
  * the bits of the IEEE operations the stored regime and the reference use (Julia sqrt and /,

@@ -20,7 +20,7 @@ using CGE: parseargs, landmarks, louvain_clust   # re-exported unchanged; wGCL* 
 using StatsBase
 using Random
 
-export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed
+export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table
 
 const LIB = get(ENV, "CGE_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "cge_jl_b200", "libcge_b200.so")))
@@ -90,6 +90,25 @@ function sample_non_edges_device(adj_edges::Array{Int,2}, n::Int, K::Int, n_sets
         ccall((:cge_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
     end
     return neg_i, neg_j
+end
+
+"""
+    read_table(fn; T=Float64, skipstart=0)
+
+Drop-in for the typed `readdlm(fn, T; skipstart)` calls of `parseargs` (auxilary.jl:86, 123,
+150-155) on large inputs (SURVEY.md 8(f) F3): the file is parsed on all host cores by
+`cge_b200_read_table` straight into the column-major matrix.  Throws where `readdlm` does (ragged
+rows, cells that are not numbers), so the node2vec `try ... catch ... skipstart=1` keeps working.
+"""
+function read_table(fn::AbstractString; T::Type=Float64, skipstart::Int=0)
+    rows = Ref{Int64}(0); cols = Ref{Int64}(0)
+    check(ccall((:cge_b200_table_dims, LIB), Cint, (Cstring, Int64, Int32, Ptr{Int64}, Ptr{Int64}),
+                fn, skipstart, 0, rows, cols))
+    out = Matrix{Float64}(undef, rows[], cols[])
+    check(ccall((:cge_b200_read_table, LIB), Cint,
+                (Cstring, Int64, Int32, Int64, Int64, Int64, Int64, Ptr{Float64}),
+                fn, skipstart, 0, rows[], cols[], 1, rows[], out))        # column-major strides
+    return T === Float64 ? out : convert.(T, out)                           # InexactError like readdlm(fn, Int)
 end
 
 """
