@@ -117,6 +117,33 @@ def oracle_sample(w, max_alphas):
     return value, dt, a_run, passes, note
 
 
+def oracle_parallel_sample(w, max_alphas):
+    """the same algorithm on ALL host cores (oracle/cge_oracle_mt.c) on the
+    same bounded prefix -- what a parallel CPU implementation would do on this box.  The reference
+    has no threading, so this is reported beside the faithful single-thread port, not instead."""
+    import oracle
+
+    t0 = time.perf_counter()
+    _, tr = oracle.wgcl_mt(w["edges"], w["ew"], w["comm"], w["emb"], w["vw"], samples=w["samples"],
+                           max_alphas=max_alphas)
+    dt = time.perf_counter() - t0
+    pairs = w["n"] * (w["n"] + 1) // 2
+    a_run, passes = int(tr.n_alpha_run), int(sum(tr.iters))
+    value, note = pairs * a_run / dt, "not extrapolated"
+    gold = os.path.join(ROOT, "tests", "golden", "oracle_example10k_exact.npz")
+    if w["n"] == 10000 and w["data"].startswith("reference example") and os.path.exists(gold):
+        it = np.load(gold)["iters"].astype(int)
+        if list(it[:a_run]) == list(tr.iters)[:a_run]:
+            # this port sweeps the pair array (passes + kernel + B) times per alpha, plus the build
+            sweeps_full = int(it.sum()) + 2 * int((it > 0).sum()) + 1
+            sweeps_sample = passes + 2 * a_run + 1
+            value = pairs * int((it > 0).sum()) / (dt * sweeps_full / sweeps_sample)
+            note = f"extrapolated linearly in O(n^2) sweeps ({sweeps_sample} of {sweeps_full})"
+    return {"value": value, "unit": UNIT, "cores": int(tr.threads), "kind": "port, multi-threaded",
+            "sample": f"oracle/cge_oracle_mt.c (same algorithm, rows dealt to {int(tr.threads)} "
+                      f"threads), first {a_run} of 40 alpha values ({passes} passes), {dt:.1f} s; {note}"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU algorithm (the line-by-line C port in oracle/; the
     Julia original cannot run in this image) on the host cores.  The reference is single-threaded
@@ -155,7 +182,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": w["data"], "config": {"workload": w["name"], "sample": sample},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(),
-                         "kind": "port", "sample": sample},
+                         "kind": "port", "sample": sample,
+                         "parallel_port": oracle_parallel_sample(w, args.ref_alphas)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -344,7 +372,8 @@ def run_b200(args):
             "threads_note": "the reference has no threading (no @threads/@spawn/Distributed in "
                             "src/): JULIA_NUM_THREADS does not change it, so one core is used",
             "sample": f"oracle/ C port of wGCL, first {a} of 40 alpha values ({sw} fixed-point "
-                      f"passes) of the same workload, {dt:.1f} s; {note}"}
+                      f"passes) of the same workload, {dt:.1f} s; {note}",
+            "parallel_port": oracle_parallel_sample(w, args.ref_alphas)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -3,5 +3,5 @@
 Nothing under cge_jl_b200/ may import this package.
 """
 from .oracle import (  # noqa: F401
-    OracleTrace, build, dist, idx, js, wgcl, wgcl_directed,
+    OracleMtTrace, OracleTrace, build, dist, host_threads, idx, js, wgcl, wgcl_directed, wgcl_mt,
 )

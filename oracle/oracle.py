@@ -31,8 +31,8 @@ class OracleTrace(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "cge_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("cge_oracle.c", "cge_oracle_mt.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libcge_oracle.so"])
     return _SO
 
@@ -167,3 +167,56 @@ def wgcl_directed(edges, eweights, comm, embed, distances, vweights, init_vweigh
                              .get(rc, f"oracle error {rc}"))
     del keep
     return out[: n_out.value].copy(), tr
+
+
+class OracleMtTrace(C.Structure):
+    _fields_ = [
+        ("n_alpha_run", C.c_int32),
+        ("iters", C.c_int32 * N_ALPHA),
+        ("div", C.c_double * N_ALPHA),
+        ("auc", C.c_double * N_ALPHA),
+        ("lo", C.c_double),
+        ("hi", C.c_double),
+        ("threads", C.c_int32),
+    ]
+
+
+def host_threads():
+    return int(_load().cge_oracle_mt_threads())
+
+
+def wgcl_mt(edges, eweights, comm, embed, vweights, samples=None, max_alphas=N_ALPHA, n_threads=0):
+    """The exact-mode undirected algorithm of :func:`wgcl` on ``n_threads`` host cores (0 = all):
+    cge_oracle_mt.c, the parallel CPU baseline of SURVEY.md 8(d).  Returns (out[7], trace)."""
+    lib = _load()
+    edges = _i64(edges)
+    src, dst = _i64(edges[:, 0]), _i64(edges[:, 1])
+    ew, cm, em, vw = _f64(eweights), _i64(np.asarray(comm).reshape(-1)), _f64(embed), _f64(vweights)
+    n = int(max(src.max(), dst.max()))
+    if cm.shape[0] != n:
+        raise AssertionError("No. communities not matching no. vertices")
+    if samples is None:
+        K, ns = 0, 1
+        pi = pj = ni = nj = np.zeros(1, dtype=np.int64)
+        pw = np.zeros(1)
+    else:
+        pi, pj, pw, ni, nj = samples
+        pi, pj, ni, nj = (np.atleast_2d(_i64(x)) for x in (pi, pj, ni, nj))
+        pw = np.atleast_2d(_f64(pw))
+        ns, K = pi.shape
+    i64, f64 = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    lib.cge_oracle_wgcl_mt.argtypes = [C.c_int64, i64, i64, f64, i64, C.c_int64, f64, C.c_int64, f64,
+                                       C.c_int64, C.c_int64, i64, i64, f64, i64, i64, C.c_int,
+                                       C.c_int, f64, C.POINTER(OracleMtTrace)]
+    lib.cge_oracle_wgcl_mt.restype = C.c_int
+    out = np.zeros(7)
+    tr = OracleMtTrace()
+    rc = lib.cge_oracle_wgcl_mt(src.shape[0], _p(src, C.c_int64), _p(dst, C.c_int64),
+                                _p(ew, C.c_double), _p(cm, C.c_int64), n, _p(em, C.c_double),
+                                em.shape[1], _p(vw, C.c_double), K, ns, _p(pi, C.c_int64),
+                                _p(pj, C.c_int64), _p(pw, C.c_double), _p(ni, C.c_int64),
+                                _p(nj, C.c_int64), int(max_alphas), int(n_threads),
+                                _p(out, C.c_double), C.byref(tr))
+    if rc != 0:
+        raise RuntimeError(f"parallel oracle error {rc}")
+    return out, tr

@@ -1,0 +1,40 @@
+"""The multi-threaded CPU baseline (oracle/cge_oracle_mt.c) against the
+sequential line-by-line oracle: same passes per alpha, same best alphas, scores equal up to the
+order of the additions."""
+import numpy as np
+import pytest
+
+import oracle
+from cge_jl_b200 import divergence as dv
+from util import load_fixture, planted_partition
+
+
+@pytest.mark.parametrize("case,threads", [("test115", 1), ("test115", 3), ("pp700", 4), ("pp700", 0)])
+def test_parallel_port_matches_the_sequential_oracle(case, threads):
+    if case == "test115":
+        edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    else:
+        edges, ew, vw, comm, emb = planted_partition(700, 5, 20, seed=705)
+    n = emb.shape[0]
+    samples = dv.draw_samples(edges, ew, n, 1500, 42, False, True)
+    ref, tr = oracle.wgcl(edges, ew, comm, emb, np.zeros(n), vw, samples=samples)
+    out, tm = oracle.wgcl_mt(edges, ew, comm, emb, vw, samples=samples, n_threads=threads)
+    assert tm.threads == (threads or oracle.host_threads())
+    assert tm.n_alpha_run == tr.n_alpha_run and list(tm.iters) == list(tr.iters)
+    assert out[0] == ref[0] and out[4] == ref[4]
+    np.testing.assert_allclose(out, ref, rtol=1e-11, atol=0)
+    np.testing.assert_allclose(np.array(tm.div), np.array(tr.div), rtol=1e-11, equal_nan=True)
+    np.testing.assert_allclose(np.array(tm.auc), np.array(tr.auc), rtol=1e-11, equal_nan=True)
+    assert tm.hi == tr.hi and tm.lo == tr.lo == 0.0
+    # deterministic for a given thread count
+    again, _ = oracle.wgcl_mt(edges, ew, comm, emb, vw, samples=samples, n_threads=threads)
+    assert np.array_equal(again, out)
+
+
+def test_parallel_port_prefix_and_no_samples():
+    edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    full, trf = oracle.wgcl(edges, ew, comm, emb, np.zeros(115), vw, max_alphas=3)
+    out, tm = oracle.wgcl_mt(edges, ew, comm, emb, vw, max_alphas=3, n_threads=2)
+    assert tm.n_alpha_run == 3 and list(tm.iters)[:3] == list(trf.iters)[:3]
+    np.testing.assert_allclose(out[:2], full[:2], rtol=1e-11)
+    assert out[4] == -1.0 and np.isinf(out[5])
