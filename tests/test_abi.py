@@ -115,3 +115,17 @@ def test_score_multi_rejects_bad_requests():
         rc = lib.cge_b200_score_multi(C.byref(p), 2, out.ctypes.data_as(C.POINTER(C.c_double)),
                                       C.byref(n_out), None)
         assert rc == _lib.ERR_CUDA
+
+
+def test_handle_entry_points_reject_a_null_handle():
+    """The sampler and the arithmetic self-test run on the device only: without a handle (no GPU,
+    no create()) they fail with an argument error instead of computing anything on the host."""
+    lib = _lib.load()
+    a, b = C.c_int64(), C.c_int64()
+    assert lib.cge_b200_selftest_math(None, 1024, 1, C.byref(a), C.byref(b)) == _lib.ERR_ARG
+    e = np.array([1, 2], dtype=np.int64)
+    o = np.zeros(4, dtype=np.int64)
+    pi = C.POINTER(C.c_int64)
+    rc = lib.cge_b200_sample_non_edges(None, 10, 1, e.ctypes.data_as(pi), e.ctypes.data_as(pi), 1, 0,
+                                       4, 1, 7, o.ctypes.data_as(pi), o.ctypes.data_as(pi), None)
+    assert rc == _lib.ERR_ARG and "sample_non_edges" in _lib.last_error()
