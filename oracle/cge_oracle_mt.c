@@ -49,6 +49,13 @@ static inline int64_t tri(int64_t k, int64_t a, int64_t b) { /* idx(k, min, max)
     return k * (i - 1) - (i - 1) * (i - 2) / 2 + j - i;
 }
 
+/* Numerics experiment for the recompute regime's planned row-norm / dot form:
+ * 0 = difference form (the reference, default); 1 = centred embedding, d^2 = n_i + n_j - 2 x_i.x_j
+ * with FMA accumulation, pairs under cancellation (d^2 < 2^-13 (n_i + n_j)) redone in the
+ * difference form, extrema taken from the same arithmetic.  tests/test_oracle_mt.py compares. */
+static int g_dist_form = 0;
+void cge_oracle_mt_set_dist_form(int form) { g_dist_form = form; }
+
 int cge_oracle_mt_threads(void) {
     long c = sysconf(_SC_NPROCESSORS_ONLN);
     return c > 0 ? (int)c : 1;
@@ -63,6 +70,7 @@ typedef struct {
     const double *eweights, *embed, *vweights, *pos_w;
     int max_alphas;
     double *vect_C, *vect_B, *D, *GD, *T, *S, *Sp, *Bp, *red;
+    double *cen, *nrm; /* dist form 1: centred embedding and squared row norms */
     double hi, alpha, diff;
     int stop, do_div;
     double *out;
@@ -90,9 +98,20 @@ static void *mt_worker(void *argp) {
         c->D[base] = 0.0;
         for (int64_t j = i + 1; j <= n; ++j) {
             double acc = 0.0;
-            for (int64_t k = 0; k < d; ++k) {
-                const double df = c->embed[(i - 1) * d + k] - c->embed[(j - 1) * d + k];
-                acc += df * df;
+            int diff_form = c->cen == NULL;
+            if (!diff_form) {
+                double g = 0.0;
+                for (int64_t k = 0; k < d; ++k) g = fma(c->cen[(i - 1) * d + k], c->cen[(j - 1) * d + k], g);
+                const double nn = c->nrm[i - 1] + c->nrm[j - 1];
+                acc = fma(-2.0, g, nn);
+                if (acc < nn * 0x1.0p-13) diff_form = 1; /* cancellation: <= 40 bits left */
+            }
+            if (diff_form) {
+                acc = 0.0;
+                for (int64_t k = 0; k < d; ++k) {
+                    const double df = c->embed[(i - 1) * d + k] - c->embed[(j - 1) * d + k];
+                    acc += df * df;
+                }
             }
             const double v = sqrt(acc);
             c->D[base + (j - i)] = v;
@@ -260,7 +279,22 @@ int cge_oracle_wgcl_mt(int64_t m, const int64_t *e_src, const int64_t *e_dst,
     c.Sp = (double *)malloc(sizeof(double) * (size_t)n * (size_t)c.nt);
     c.Bp = (double *)malloc(sizeof(double) * (size_t)c.vect_len * (size_t)c.nt);
     c.red = (double *)calloc((size_t)c.nt, sizeof(double));
+    if (g_dist_form == 1) {
+        c.cen = (double *)malloc(sizeof(double) * (size_t)n * (size_t)d);
+        c.nrm = (double *)calloc((size_t)n, sizeof(double));
+        if (c.cen && c.nrm) {
+            for (int64_t k = 0; k < d; ++k) {
+                double mean = 0.0;
+                for (int64_t i = 0; i < n; ++i) mean += embed[i * d + k];
+                mean /= (double)n;
+                for (int64_t i = 0; i < n; ++i) c.cen[i * d + k] = embed[i * d + k] - mean;
+            }
+            for (int64_t i = 0; i < n; ++i)
+                for (int64_t k = 0; k < d; ++k) c.nrm[i] = fma(c.cen[i * d + k], c.cen[i * d + k], c.nrm[i]);
+        }
+    }
     int rc = 0;
+    if (g_dist_form == 1 && (!c.cen || !c.nrm)) rc = -4;
     if (!c.vect_C || !c.vect_B || !c.D || !c.GD || !c.T || !c.S || !c.Sp || !c.Bp || !c.red) rc = -4;
     if (!rc) {
         for (int64_t i = 0; i < m; ++i) /* :59-63 */
@@ -290,6 +324,6 @@ int cge_oracle_wgcl_mt(int64_t m, const int64_t *e_src, const int64_t *e_dst,
         free(args);
     }
     free(c.vect_C); free(c.vect_B); free(c.D); free(c.GD); free(c.T); free(c.S); free(c.Sp);
-    free(c.Bp); free(c.red);
+    free(c.Bp); free(c.red); free(c.cen); free(c.nrm);
     return rc;
 }

@@ -185,10 +185,16 @@ def host_threads():
     return int(_load().cge_oracle_mt_threads())
 
 
-def wgcl_mt(edges, eweights, comm, embed, vweights, samples=None, max_alphas=N_ALPHA, n_threads=0):
+def wgcl_mt(edges, eweights, comm, embed, vweights, samples=None, max_alphas=N_ALPHA, n_threads=0,
+            dist_form=0):
     """The exact-mode undirected algorithm of :func:`wgcl` on ``n_threads`` host cores (0 = all):
-    cge_oracle_mt.c, the parallel CPU baseline of SURVEY.md 8(d).  Returns (out[7], trace)."""
+    cge_oracle_mt.c, the parallel CPU baseline of SURVEY.md 8(d).  Returns (out[7], trace).
+
+    ``dist_form=1`` is the numerics experiment for the recompute regime's planned row-norm / dot
+    form (centred embedding, FMA dot products, difference form under cancellation, extrema from
+    the same arithmetic); 0 is the reference's difference form."""
     lib = _load()
+    lib.cge_oracle_mt_set_dist_form(int(dist_form))
     edges = _i64(edges)
     src, dst = _i64(edges[:, 0]), _i64(edges[:, 1])
     ew, cm, em, vw = _f64(eweights), _i64(np.asarray(comm).reshape(-1)), _f64(embed), _f64(vweights)
@@ -217,6 +223,7 @@ def wgcl_mt(edges, eweights, comm, embed, vweights, samples=None, max_alphas=N_A
                                 _p(pj, C.c_int64), _p(pw, C.c_double), _p(ni, C.c_int64),
                                 _p(nj, C.c_int64), int(max_alphas), int(n_threads),
                                 _p(out, C.c_double), C.byref(tr))
+    lib.cge_oracle_mt_set_dist_form(0)
     if rc != 0:
         raise RuntimeError(f"parallel oracle error {rc}")
     return out, tr
