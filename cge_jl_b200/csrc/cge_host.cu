@@ -540,6 +540,9 @@ struct cge_b200_handle {
     // device
     DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
         sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out, fpres;
+    // recompute regime, row-norm / dot form (CGE_B200_RC_FORM=dot): centred embedding, row norms
+    DevBuf emb_c, nrm;
+    bool rc_dot = false;
     // tensor-core diameter filter (landmark mode, large original graphs)
     DevBuf diam_strips, diam_packed, diam_norms, diam_tilemax, diam_list, diam_ctr, diam_mean;
     int diam_n_strips = 0;
@@ -775,6 +778,28 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         if ((rc = h->q.ensure(q_bytes))) return rc;
     } else {
         h->q.release();
+    }
+    // Opt-in: distances of the recompute regime from d^2 = n_i + n_j - 2 x_i.x_j on the centred
+    // embedding (cge_recompute.cu, DOT variants) instead of the difference form.
+    const char *rc_form = getenv("CGE_B200_RC_FORM");
+    h->rc_dot = h->regime == CGE_B200_REGIME_RECOMPUTE && rc_form && std::strcmp(rc_form, "dot") == 0;
+    if (h->rc_dot) {
+        std::vector<double> cen((size_t)(np * dp), 0.0), nrm((size_t)np, 0.0);
+        for (int64_t c = 0; c < p->d; ++c) {
+            double mean = 0.0;
+            for (int64_t r = 0; r < n; ++r) mean += emb[(size_t)(r * dp + c)];
+            mean /= (double)n;
+            for (int64_t r = 0; r < n; ++r) cen[(size_t)(r * dp + c)] = emb[(size_t)(r * dp + c)] - mean;
+        }
+        for (int64_t r = 0; r < n; ++r) {
+            double acc = 0.0;
+            for (int64_t c = 0; c < dp; ++c) acc = std::fma(cen[(size_t)(r * dp + c)], cen[(size_t)(r * dp + c)], acc);
+            nrm[(size_t)r] = acc;
+        }
+        if ((rc = upload_vec(h->emb_c, cen.data(), cen.size() * 8, st))) return rc;
+        if ((rc = upload_vec(h->nrm, nrm.data(), nrm.size() * 8, st))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));  // cen, nrm are locals
+        if (getenv("CGE_B200_PHASES")) fprintf(stderr, "[cge_b200] recompute regime: row-norm/dot form\n");
     }
     const size_t part_bytes = (size_t)h->nb * (size_t)np * 8;
     if ((rc = h->partA.ensure(part_bytes))) return rc;
@@ -1074,7 +1099,20 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                                                           h->dist.as<double>(), n,
                                                           h->tile_ij.as<int2>(), tb, te,
                                                           h->q.as<double>(), lohi);
-        else  // recompute regime: only the extrema are needed up front
+        else if (h->rc_dot) {  // ... in the arithmetic the passes will use
+            SweepArgs E = {};
+            E.tile_ij = h->tile_ij.as<int2>();
+            E.tile_begin = tb;
+            E.tile_end = te;
+            E.n = n;
+            E.np = np;
+            E.dp = dp;
+            E.emb = h->emb.as<double>();
+            E.emb_c = h->emb_c.as<double>();
+            E.nrm = h->nrm.as<double>();
+            E.diag = h->dist.as<double>();
+            launch_extrema_rc(grid, st, E, lohi);
+        } else  // recompute regime: only the extrema are needed up front
             k_build_dist<false><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
                                                            h->dist.as<double>(), n,
                                                            h->tile_ij.as<int2>(), tb, te, nullptr,
@@ -1099,10 +1137,17 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         const double *dg = h->landmark ? nullptr : h->dist.as<double>();
         const unsigned long long *lh = h->landmark ? lohi + 2 : lohi;
         const int blocks = (int)((SK + 255) / 256);
-        k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh,
-                                           h->landmark, SK, h->s_pq.as<double>());
-        k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_nda.as<int>(), h->s_ndb.as<int>(), dg, lh,
-                                           h->landmark, SK, h->s_nq.as<double>());
+        if (h->rc_dot && !h->landmark) {  // the sampled pairs get the bits the passes use
+            launch_sample_q_dot(h->emb_c.as<double>(), h->nrm.as<double>(), e, dp, h->s_pda.as<int>(),
+                                h->s_pdb.as<int>(), dg, lh, SK, h->s_pq.as<double>(), st);
+            launch_sample_q_dot(h->emb_c.as<double>(), h->nrm.as<double>(), e, dp, h->s_nda.as<int>(),
+                                h->s_ndb.as<int>(), dg, lh, SK, h->s_nq.as<double>(), st);
+        } else {
+            k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh,
+                                               h->landmark, SK, h->s_pq.as<double>());
+            k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_nda.as<int>(), h->s_ndb.as<int>(), dg, lh,
+                                               h->landmark, SK, h->s_nq.as<double>());
+        }
         h->launches += 2;
     }
     // ---- T (divergence.jl:118 / 399-402), partial slots ----
@@ -1166,6 +1211,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         CUDA_TRY(cudaMemsetAsync(A.phase_ns, 0, 64, st));
     }
     A.emb = h->emb.as<double>();
+    A.emb_c = h->rc_dot ? h->emb_c.as<double>() : nullptr;
+    A.nrm = h->rc_dot ? h->nrm.as<double>() : nullptr;
     A.diag = h->dist.as<double>();
     A.lohi = lohi;
     A.dp = dp;
@@ -1205,7 +1252,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         if (driver == CGE_B200_DRIVER_PERSISTENT || driver == CGE_B200_DRIVER_RING) {
             // one cooperative launch runs every pass of this alpha
             const bool ring = stored && driver == CGE_B200_DRIVER_RING;
-            const void *fn = !stored ? fp_kernel_rc(h->directed)
+            const void *fn = !stored ? fp_kernel_rc(h->directed, h->rc_dot)
                              : ring  ? fp_ring_kernel(m, h->directed)
                              : small ? fp_kernel_rt(h->directed)
                                      : fp_kernel(m, h->directed);
@@ -1477,7 +1524,7 @@ void cge_b200_destroy(cge_b200_handle *h) {
     for (DevBuf *b :
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
-          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
+          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->emb_c, &h->nrm, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
           &h->diam_list, &h->diam_ctr, &h->diam_mean, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
           &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})

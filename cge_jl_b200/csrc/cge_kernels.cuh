@@ -52,6 +52,8 @@ struct SweepArgs {
     long long resident_tiles;  // local tiles [0, resident_tiles) are kept in L2 (evict_last)
     // recompute regime only
     const double *emb;     // [np][dp] sorted, zero-padded embedding
+    const double *emb_c = nullptr;  // row-norm / dot form only: the same, centred at the mean
+    const double *nrm = nullptr;    //   and its squared row norms [np]
     const double *diag;    // [np] D_ii (divergence.jl:85-86)
     const unsigned long long *lohi;  // bit patterns of lo, hi (divergence.jl:92)
     int dp, m;             // padded dimension; exponent m = 4*alpha
@@ -723,7 +725,12 @@ void launch_select_candidates(const float *tile_max, long long n_tiles, const un
                               cudaStream_t st);
 // recompute regime (cge_recompute.cu): kind as in launch_tiles, exponent taken from a.m
 void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
-const void *fp_kernel_rc(int directed);
+const void *fp_kernel_rc(int directed, int dot);
+void launch_extrema_rc(int grid, cudaStream_t stream, const SweepArgs &a, unsigned long long *lohi);
+void launch_sample_q_dot(const double *emb_c, const double *nrm, const double *emb, int dp,
+                         const int *ia, const int *ib, const double *diag,
+                         const unsigned long long *lohi, long long count, double *out,
+                         cudaStream_t stream);
 size_t rc_smem_bytes();  // dynamic shared memory of every recompute kernel
 void launch_selftest_math(long long n, unsigned long long seed, unsigned long long *out, int grid,
                           cudaStream_t st);
