@@ -314,7 +314,7 @@ def run_b200(args):
     kname = {1: "k_sweep<M,false> (one fixed-point pass per launch)",
              2: "k_fixed_point<M,false> (all passes of one alpha per cooperative launch)",
              3: "k_fixed_point_ring<M,false> (all passes of one alpha, cp.async.bulk ring)"}
-    if int(stats.regime) == 2:
+    if int(stats.regime) in (2, 3):
         kname = {1: "k_sweep_rc<false>", 2: "k_fixed_point_rc<false>", 3: "k_fixed_point_rc<false>"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -327,7 +327,7 @@ def run_b200(args):
                    "l2": "inputs larger than L2 (q matrix %.0f MB per GPU vs 126 MB L2)"
                          % (stats.matrix_bytes / 1e6),
                    "driver": {1: "hostloop", 2: "persistent", 3: "ring"}.get(int(stats.driver), "?"),
-                   "regime": {1: "stored", 2: "recompute"}.get(int(stats.regime), "?"),
+                   "regime": {1: "stored", 2: "recompute", 3: "recompute, row-norm/dot form"}.get(int(stats.regime), "?"),
                    "result": [float(x) for x in out],
                    "device_ms_per_step": float(np.mean(ev_ms)),
                    "ms_breakdown_last_step": {
@@ -350,7 +350,7 @@ def run_b200(args):
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"
                                     if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
     }
-    if int(stats.regime) == 2:
+    if int(stats.regime) in (2, 3):
         # recompute regime: FP64-pipe roofline, algorithmic work (2d + 6) flop per pair and pass
         # (SURVEY.md 8(d)); peak = FP64 FMA throughput measured on this device by the library
         d_emb = w["emb"].shape[1]
@@ -386,7 +386,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--driver", type=int, default=0, help="0 auto, 1 host loop, 2 persistent")
-    ap.add_argument("--regime", type=int, default=0, help="0 auto, 1 stored, 2 recompute")
+    ap.add_argument("--regime", type=int, default=0, help="0 auto, 1 stored, 2 recompute, 3 recompute with the row-norm/dot form")
     ap.add_argument("--ref-alphas", type=int, default=2,
                     help="alpha values per CPU sample (bounds the CPU baseline's run time)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -761,7 +761,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     }
     const size_t local_tiles = (size_t)(h->tile_end - h->tile_begin);
     const size_t q_bytes = std::max<size_t>(local_tiles, 1) * TILE_ELEMS * 8;
-    h->regime = p->regime;
+    h->regime = p->regime == CGE_B200_REGIME_RECOMPUTE_DOT ? CGE_B200_REGIME_RECOMPUTE : p->regime;
     if (h->regime == CGE_B200_REGIME_AUTO && h->q.cap >= q_bytes) {
         h->regime = CGE_B200_REGIME_STORED;  // the handle already holds a large enough matrix
     } else if (h->regime == CGE_B200_REGIME_AUTO) {
@@ -779,10 +779,13 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     } else {
         h->q.release();
     }
-    // Opt-in: distances of the recompute regime from d^2 = n_i + n_j - 2 x_i.x_j on the centred
-    // embedding (cge_recompute.cu, DOT variants) instead of the difference form.
+    // Opt-in (regime RECOMPUTE_DOT, or CGE_B200_RC_FORM=dot for hosts that cannot set the field):
+    // distances of the recompute regime from d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding
+    // (cge_recompute.cu, DOT variants) instead of the difference form.
     const char *rc_form = getenv("CGE_B200_RC_FORM");
-    h->rc_dot = h->regime == CGE_B200_REGIME_RECOMPUTE && rc_form && std::strcmp(rc_form, "dot") == 0;
+    h->rc_dot = h->regime == CGE_B200_REGIME_RECOMPUTE &&
+                (p->regime == CGE_B200_REGIME_RECOMPUTE_DOT ||
+                 (rc_form && std::strcmp(rc_form, "dot") == 0));
     if (h->rc_dot) {
         std::vector<double> cen((size_t)(np * dp), 0.0), nrm((size_t)np, 0.0);
         for (int64_t c = 0; c < p->d; ++c) {
@@ -1051,7 +1054,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             ? CGE_B200_DRIVER_PERSISTENT  // measured: 65.3 us/pass vs 72.2 for the TMA ring (r01)
             : h->driver;
     S.driver = driver;
-    S.regime = h->regime;
+    S.regime = h->rc_dot ? CGE_B200_REGIME_RECOMPUTE_DOT : h->regime;
     const bool stored = h->regime == CGE_B200_REGIME_STORED;
     // small problems (fewer tiles than resident CTAs): one run-time-exponent kernel for the whole
     // alpha grid instead of one instantiation per alpha (first-use load time, see powm_any)

@@ -53,7 +53,12 @@ enum {
 enum {
     CGE_B200_REGIME_AUTO = 0,         /* stored when it fits in free HBM, else recompute */
     CGE_B200_REGIME_STORED = 1,       /* q = (1-D)^(1/4) kept in HBM: 8 B per pair and pass, HBM bound */
-    CGE_B200_REGIME_RECOMPUTE = 2     /* distances re-derived from the embedding every pass: FP64 bound */
+    CGE_B200_REGIME_RECOMPUTE = 2,    /* distances re-derived from the embedding every pass: FP64 bound */
+    CGE_B200_REGIME_RECOMPUTE_DOT = 3 /* the same with d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding
+                                         (one FMA per dimension and pair; pairs under cancellation use
+                                         the difference form; extrema and sampled pairs share the
+                                         arithmetic).  Opt-in, never chosen by AUTO; also selected by
+                                         CGE_B200_RC_FORM=dot when the regime resolves to RECOMPUTE */
 };
 
 /*

@@ -30,7 +30,7 @@ def run_pair(scorer, directed, edges, ew, comm, emb, dist, vw, lm_args=None, spl
     out, stats = f_gpu(edges, ew, comm, emb, dist, vw, init_vw, v2l, init_edges, init_ew,
                        init_emb, split, seed, K, False, samples=samples, return_stats=True,
                        scorer=scorer, driver=driver, regime=regime)
-    assert driver == 0 or stats.driver == driver or regime == 2
+    assert driver == 0 or stats.driver == driver or regime >= 2
     assert stats.regime == (regime or 1)
     f_ref = oracle.wgcl_directed if directed else oracle.wgcl
     ref, tr = f_ref(edges, ew, comm, emb, dist, vw, init_vw if lm_args else None,
@@ -153,6 +153,22 @@ def test_recompute_regime(scorer, directed, n, k, d, driver):
     out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
                                    driver=driver, regime=2)
     assert stats.matrix_bytes == 0
+    assert_parity(out, stats, ref, tr)
+
+
+@pytest.mark.parametrize("directed,n,k,d", [(False, 115, 0, 0), (False, 700, 5, 20),
+                                            (True, 520, 7, 33)])
+def test_recompute_row_norm_dot_form(scorer, directed, n, k, d):
+    """Regime 3: the recompute regime with d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding
+    (extrema and sampled pairs in the same arithmetic); same parity bars against the oracle."""
+    if k == 0:
+        edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    else:
+        edges, ew, vw, comm, emb = planted_partition(n, k, d, seed=n + k, directed=directed,
+                                                     weighted=True)
+    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
+                                   driver=2, regime=3)
+    assert stats.matrix_bytes == 0 and stats.regime == 3
     assert_parity(out, stats, ref, tr)
 
 

@@ -67,6 +67,24 @@ def test_stored_and_recompute_regimes_agree(scorer, directed, d):
                                equal_nan=True)
 
 
+@pytest.mark.parametrize("directed,d", [(False, 40), (True, 24)])
+def test_stored_and_row_norm_dot_form_agree(scorer, directed, d):
+    """Regime 3 against the stored regime on 300 tiles, with an exactly duplicated and a 1e-9-close
+    embedding row (the pairs the dot form hands back to the difference form)."""
+    n = 3001
+    data = planted_partition(n, k=9, d=d, seed=77, directed=directed, weighted=True)
+    data[4][1234] = data[4][77]
+    data[4][55] = data[4][56] + 1e-9
+    samples = dv.draw_samples(data[0], data[1], n, 3000, 42, directed, True)
+    a, sa = _run(scorer, directed, data, samples, 2, 1, n)
+    b, sb = _run(scorer, directed, data, samples, 2, 3, n)
+    assert sa.regime == 1 and sb.regime == 3 and sb.matrix_bytes == 0
+    assert list(sa.iters) == list(sb.iters) and a[0] == b[0] and a[4] == b[4]
+    np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(np.array(list(sb.div)), np.array(list(sa.div)), rtol=1e-11,
+                               equal_nan=True)
+
+
 def test_q_matrix_symmetric_and_in_range_at_scale(scorer):
     n = 2500
     data = planted_partition(n, k=6, d=24, seed=5)
