@@ -129,3 +129,47 @@ def test_handle_entry_points_reject_a_null_handle():
     rc = lib.cge_b200_sample_non_edges(None, 10, 1, e.ctypes.data_as(pi), e.ctypes.data_as(pi), 1, 0,
                                        4, 1, 7, o.ctypes.data_as(pi), o.ctypes.data_as(pi), None)
     assert rc == _lib.ERR_ARG and "sample_non_edges" in _lib.last_error()
+
+
+C_CLIENT = r"""
+#include <stdio.h>
+#include <string.h>
+#include "cge_b200.h"
+/* a plain-C host: what a cgo / ccall / JNI stub does, without Python in between */
+int main(int argc, char **argv) {
+    int a, b, c;
+    cge_b200_version(&a, &b, &c);
+    int64_t nt, t0, t1, rows, cols;
+    if (cge_b200_shard_plan(10000, 1, 4, &nt, &t0, &t1) != CGE_B200_OK) return 2;
+    if (cge_b200_table_dims(argv[1], 0, 2, &rows, &cols) != CGE_B200_OK) return 3;
+    double m[6];
+    if (rows != 2 || cols != 3) return 4;
+    if (cge_b200_read_table(argv[1], 0, 2, rows, cols, 1, rows, m) != CGE_B200_OK) return 5; /* column-major */
+    cge_b200_problem p;
+    memset(&p, 0, sizeof p);
+    p.struct_size = (int32_t)sizeof p;
+    double out[7];
+    int32_t n_out = 0;
+    int rc = cge_b200_device_count() > 0 ? CGE_B200_ERR_CUDA : cge_b200_score(&p, out, &n_out, NULL);
+    printf("%d.%d.%d %lld %lld %lld %g %g %g %g %g %g %d %s\n", a, b, c, (long long)nt, (long long)t0,
+           (long long)t1, m[0], m[1], m[2], m[3], m[4], m[5], rc, cge_b200_last_error());
+    return 0;
+}
+"""
+
+
+def test_a_plain_c_host_can_use_the_library(tmp_path):
+    """The boundary is a C ABI: a C program includes cge_b200.h, links libcge_b200.so and calls it."""
+    (tmp_path / "client.c").write_text(C_CLIENT)
+    (tmp_path / "t.txt").write_text("1 2 3\n4 5 6\n")
+    exe = tmp_path / "client"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.dirname(HEADER),
+                           str(tmp_path / "client.c"), "-o", str(exe), "-L", libdir,
+                           "-l:libcge_b200.so", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.check_output([str(exe), str(tmp_path / "t.txt")], text=True).split(" ", 13)
+    assert out[0] == "0.1.0"
+    nt, t0, t1 = (int(x) for x in out[1:4])
+    assert (nt, t0, t1) == _lib.shard_plan(10000, 1, 4)
+    assert [float(x) for x in out[4:10]] == [1.0, 4.0, 2.0, 5.0, 3.0, 6.0]  # column-major fill
+    assert int(out[10]) == _lib.ERR_CUDA                                     # no device: no fallback
