@@ -90,6 +90,7 @@ def main():
     ap.add_argument("--samples", type=int, default=10000)
     ap.add_argument("--no-p2p", action="store_true")
     ap.add_argument("--regime", type=int, default=0)
+    ap.add_argument("--driver", type=int, default=0, help="0 auto, 1 host loop, 2 persistent, 3 TMA ring")
     ap.add_argument("--max-alphas", type=int, default=0)
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -125,7 +126,7 @@ def main():
             handles = [None] * world
             dist.all_gather_object(handles, sc.p2p_export(n_scored))
             sc.p2p_import(handles)
-    p, keep = dv.make_problem(*prob, False, c["directed"], samples, args.max_alphas, 0, args.regime)
+    p, keep = dv.make_problem(*prob, False, c["directed"], samples, args.max_alphas, args.driver, args.regime)
     t0 = time.perf_counter()
     sc.upload(p, keep)
     t_upload = time.perf_counter() - t0
