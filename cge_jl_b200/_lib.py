@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libcge_b200.so")
 OK, ERR_ARG, ERR_ASSERT_COMM, ERR_ASSERT_DIST, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_STATE = (
     0, -1, -2, -3, -4, -5, -6, -7)
 DRIVER_AUTO, DRIVER_HOSTLOOP, DRIVER_PERSISTENT, DRIVER_RING = 0, 1, 2, 3
-REGIME_AUTO, REGIME_STORED, REGIME_RECOMPUTE = 0, 1, 2
+REGIME_AUTO, REGIME_STORED, REGIME_RECOMPUTE, REGIME_RECOMPUTE_DOT, REGIME_RECOMPUTE_DIFF = 0, 1, 2, 3, 4
 
 _pd = C.POINTER(C.c_double)
 _pi = C.POINTER(C.c_int64)
@@ -69,7 +69,7 @@ EXPORTS = [
     "cge_b200_shard_plan", "cge_b200_debug_read", "cge_b200_p2p_handle_size",
     "cge_b200_p2p_export", "cge_b200_p2p_import", "cge_b200_measure_fp64_peak",
     "cge_b200_selftest_math", "cge_b200_sample_non_edges", "cge_b200_table_dims",
-    "cge_b200_read_table",
+    "cge_b200_read_table", "cge_b200_measure_fp64_pipes",
 ]
 
 _lib = None
@@ -106,6 +106,7 @@ def load():
     lib.cge_b200_p2p_export.argtypes = [vp, C.c_int64, vp]
     lib.cge_b200_p2p_import.argtypes = [vp, vp]
     lib.cge_b200_measure_fp64_peak.argtypes = [vp, _pd]
+    lib.cge_b200_measure_fp64_pipes.argtypes = [vp, _pd]
     lib.cge_b200_sample_non_edges.argtypes = [vp, C.c_int64, C.c_int64, _pi, _pi, C.c_int32, C.c_int32,
                                               C.c_int64, C.c_int64, C.c_uint64, _pi, _pi, _pd]
     lib.cge_b200_table_dims.argtypes = [C.c_char_p, C.c_int64, C.c_int32, _pi, _pi]

@@ -75,6 +75,12 @@ def _find(argv, flag):
         return None
 
 
+def _require(cond, msg):
+    """The reference's ``@assert`` (auxilary.jl:81-158): raises AssertionError also under ``python -O``."""
+    if not cond:
+        raise AssertionError(msg)
+
+
 def _parse(argv):
     methods = {
         "rss": _lm.split_cluster_rss,
@@ -89,16 +95,16 @@ def _parse(argv):
 
     # edgelist (auxilary.jl:80-112)
     i = _find(argv, "-g")
-    assert i is not None, "Edgelist file is required"
+    _require(i is not None, "Edgelist file is required")
     fn_edges = argv[i + 1]
-    assert os.path.isfile(fn_edges), f"{fn_edges} is not a file"
+    _require(os.path.isfile(fn_edges), f"{fn_edges} is not a file")
     raw = _readdlm(fn_edges, np.float64)
     rows, no_cols = raw.shape
     if verbose:
         print(f"{no_cols} columns and {rows} rows in edgelist file.")
-    assert no_cols in (2, 3), "Expected 2 or 3 columns in edgelist file"
+    _require(no_cols in (2, 3), "Expected 2 or 3 columns in edgelist file")
     v_min = raw[:, :2].min()
-    assert v_min in (0.0, 1.0), "Vertices should be either 0-based or 1-based"
+    _require(v_min in (0.0, 1.0), "Vertices should be either 0-based or 1-based")
     if v_min == 0.0:
         raw[:, :2] += 1.0
     no_vertices = int(raw[:, :2].max())
@@ -129,18 +135,15 @@ def _parse(argv):
         fn_comm = fn_edges + ".ecg"
     comm = _readdlm(fn_comm, np.int64)
     comm_rows, c_cols = comm.shape
-    assert comm_rows == no_vertices, (
-        f"No. communities ({comm_rows}) differ from no. nodes ({no_vertices})"
-    )
-    assert c_cols in (1, 2), (
-        f"Expected 1 or 2 columns in communities file, but encountered {c_cols}."
-    )
+    _require(comm_rows == no_vertices,
+             f"No. communities ({comm_rows}) differ from no. nodes ({no_vertices})")
+    _require(c_cols in (1, 2),
+             f"Expected 1 or 2 columns in communities file, but encountered {c_cols}.")
     if c_cols == 2:
         comm = comm[np.argsort(comm[:, 0], kind="stable"), 1].reshape(-1, 1)
     c_min = comm.min()
-    assert c_min in (0, 1), (
-        f"Communities should be either 0-based or 1-based, but are {c_min} based."
-    )
+    _require(c_min in (0, 1),
+             f"Communities should be either 0-based or 1-based, but are {c_min} based.")
     if c_min == 0:
         comm = comm + 1
     comm = np.ascontiguousarray(comm.reshape(-1, 1))
@@ -149,18 +152,17 @@ def _parse(argv):
 
     # embedding (auxilary.jl:144-168)
     i = _find(argv, "-e")
-    assert i is not None, "Embedding file is required"
+    _require(i is not None, "Embedding file is required")
     fn_embed = argv[i + 1]
-    assert os.path.isfile(fn_embed), f"{fn_embed} is not a file"
+    _require(os.path.isfile(fn_embed), f"{fn_embed} is not a file")
     try:
         embedding = _readdlm(fn_embed, np.float64)
     except ValueError:
         if verbose:
             print("Embedding in node2vec format. Loading without first line.")
         embedding = _readdlm(fn_embed, np.float64, skiprows=1)
-    assert no_vertices == embedding.shape[0], (
-        "No. rows in embedding and no. vertices in a graph differ."
-    )
+    _require(no_vertices == embedding.shape[0],
+             "No. rows in embedding and no. vertices in a graph differ.")
     first = embedding[:, 0]
     if np.all(first == np.round(first)):
         if verbose:

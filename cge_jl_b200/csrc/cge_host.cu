@@ -8,6 +8,7 @@
 // section 8(a).
 #include "../../include/cge_b200.h"
 #include "cge_kernels.cuh"
+#include "cge_rc.cuh"
 #include "cge_ring.cuh"
 
 #include <dlfcn.h>
@@ -540,9 +541,13 @@ struct cge_b200_handle {
     // device
     DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
         sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out, fpres;
-    // recompute regime, row-norm / dot form (CGE_B200_RC_FORM=dot): centred embedding, row norms
-    DevBuf emb_c, nrm;
+    // recompute regime: super-tile table, operand image (centred for the row-norm / dot form), row norms
+    DevBuf st_ij, opT, nrm, rc_mean;
     bool rc_dot = false;
+    int regime_reported = CGE_B200_REGIME_STORED;
+    int sb = 1;                          // tiles per super-block side
+    int64_t nsb = 0, n_st = 0, st_begin = 0, st_end = 0;
+    int srow_begin = 0, srow_end = -1;
     // tensor-core diameter filter (landmark mode, large original graphs)
     DevBuf diam_strips, diam_packed, diam_norms, diam_tilemax, diam_list, diam_ctr, diam_mean;
     int diam_n_strips = 0;
@@ -594,6 +599,34 @@ static std::vector<int2> make_tile_table(int64_t nb) {
     return t;
 }
 
+static int nccl_check(int rc, const char *what);
+
+// max of a small host integer over the ranks (the in-process group, or NCCL on a device word)
+static int agree_max_across_ranks(cge_b200_handle *h, int *value) {
+    if (h->group) {
+        LocalGroup &G = *h->group;
+        G.lohi[2 * h->rank] = (unsigned long long)*value;
+        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        unsigned long long mx = 0;
+        for (int r = 0; r < G.n; ++r) mx = std::max(mx, G.lohi[2 * r]);
+        if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        *value = (int)mx;
+        return 0;
+    }
+    if (!h->nccl_comm) return fail(CGE_B200_ERR_STATE, "multi-rank handle without a communicator");
+    if (int rc = h->slots.ensure(128)) return rc;
+    unsigned long long v = (unsigned long long)*value;
+    CUDA_TRY(cudaMemcpyAsync(h->slots.p, &v, 8, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = nccl_check(g_nccl.AllReduce(h->slots.p, h->slots.p, 1, kNcclU64, kNcclMax,
+                                             h->nccl_comm, h->stream),
+                            "ncclAllReduce(regime)"))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(&v, h->slots.p, 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    *value = (int)v;
+    return 0;
+}
+
 static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     auto t0 = std::chrono::steady_clock::now();
     const bool trace = getenv("CGE_B200_PHASES") && atoi(getenv("CGE_B200_PHASES"));
@@ -638,6 +671,9 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
     h->np = h->nb * TILE;
     h->K = p->n_samples;
     h->n_sets = p->n_samples > 0 ? std::max<int64_t>(p->n_sets, 1) : 1;
+    // one set for every alpha, or one set per evaluated alpha (the run indexes set m-1 for alpha m)
+    if (h->n_sets != 1 && h->n_sets < h->max_alphas)
+        return fail(CGE_B200_ERR_ARG, "n_sets must be 1 or at least the number of alpha values evaluated");
     h->n_full = p->n_full;
     // communities, 0-based; n_parts = maximum(comm) (divergence.jl:51)
     int64_t k = 0;
@@ -751,17 +787,15 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         if ((rc = upload_vec(h->T0b, Tb.data(), Tb.size() * 8, st))) return rc;
     }
     lap("per-vertex arrays uploaded");
-    // tile table and this rank's share
+    // this rank's share of the tile sequence, regime
     h->n_tiles = h->nb * (h->nb + 1) / 2;
     shard_range(h->n_tiles, h->rank, h->n_ranks, &h->tile_begin, &h->tile_end);
-    {
-        std::vector<int2> tij = make_tile_table(h->nb);
-        if ((rc = upload_vec(h->tile_ij, tij.data(), tij.size() * sizeof(int2), st))) return rc;
-        CUDA_TRY(cudaStreamSynchronize(st));  // tij is a local
-    }
     const size_t local_tiles = (size_t)(h->tile_end - h->tile_begin);
     const size_t q_bytes = std::max<size_t>(local_tiles, 1) * TILE_ELEMS * 8;
-    h->regime = p->regime == CGE_B200_REGIME_RECOMPUTE_DOT ? CGE_B200_REGIME_RECOMPUTE : p->regime;
+    const int want = p->regime;
+    if (want < CGE_B200_REGIME_AUTO || want > CGE_B200_REGIME_RECOMPUTE_DIFF)
+        return fail(CGE_B200_ERR_ARG, "unknown regime");
+    h->regime = want >= CGE_B200_REGIME_RECOMPUTE ? CGE_B200_REGIME_RECOMPUTE : want;
     if (h->regime == CGE_B200_REGIME_AUTO && h->q.cap >= q_bytes) {
         h->regime = CGE_B200_REGIME_STORED;  // the handle already holds a large enough matrix
     } else if (h->regime == CGE_B200_REGIME_AUTO) {
@@ -769,42 +803,93 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         // (cudaMemGetInfo costs milliseconds: only asked when the matrix has to be (re)allocated)
         size_t free_b = 0, total_b = 0;
         CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-        const size_t avail = free_b + h->q.cap;
+        const size_t avail = free_b + h->q.cap + h->partA.cap + h->partB.cap;
         const size_t other = (size_t)h->nb * (size_t)np * 8 * (h->directed ? 2 : 1) + ((size_t)2 << 30);
         h->regime = q_bytes + other + total_b / 20 <= avail ? CGE_B200_REGIME_STORED
                                                             : CGE_B200_REGIME_RECOMPUTE;
     }
+    // every rank must run the same regime (a rank that alone falls back to recomputing would leave
+    // its peers polling the exchange records of a kernel that never starts): the ranks agree on
+    // the larger code, i.e. recompute as soon as one of them cannot store its share
+    if (h->n_ranks > 1 && want == CGE_B200_REGIME_AUTO)
+        if ((rc = agree_max_across_ranks(h, &h->regime))) return rc;
     if (h->regime == CGE_B200_REGIME_STORED) {
         if ((rc = h->q.ensure(q_bytes))) return rc;
     } else {
         h->q.release();
     }
-    // Opt-in (regime RECOMPUTE_DOT, or CGE_B200_RC_FORM=dot for hosts that cannot set the field):
-    // distances of the recompute regime from d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding
-    // (cge_recompute.cu, DOT variants) instead of the difference form.
+    const bool stored = h->regime == CGE_B200_REGIME_STORED;
+    // Distances of the recompute regime: d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding
+    // (cge_recompute.cu) unless the difference form of the reference is asked for (regime
+    // RECOMPUTE_DIFF, or CGE_B200_RC_FORM=diff for hosts that cannot set the field).
     const char *rc_form = getenv("CGE_B200_RC_FORM");
-    h->rc_dot = h->regime == CGE_B200_REGIME_RECOMPUTE &&
-                (p->regime == CGE_B200_REGIME_RECOMPUTE_DOT ||
-                 (rc_form && std::strcmp(rc_form, "dot") == 0));
-    if (h->rc_dot) {
-        std::vector<double> cen((size_t)(np * dp), 0.0), nrm((size_t)np, 0.0);
-        for (int64_t c = 0; c < p->d; ++c) {
-            double mean = 0.0;
-            for (int64_t r = 0; r < n; ++r) mean += emb[(size_t)(r * dp + c)];
-            mean /= (double)n;
-            for (int64_t r = 0; r < n; ++r) cen[(size_t)(r * dp + c)] = emb[(size_t)(r * dp + c)] - mean;
-        }
-        for (int64_t r = 0; r < n; ++r) {
-            double acc = 0.0;
-            for (int64_t c = 0; c < dp; ++c) acc = std::fma(cen[(size_t)(r * dp + c)], cen[(size_t)(r * dp + c)], acc);
-            nrm[(size_t)r] = acc;
-        }
-        if ((rc = upload_vec(h->emb_c, cen.data(), cen.size() * 8, st))) return rc;
-        if ((rc = upload_vec(h->nrm, nrm.data(), nrm.size() * 8, st))) return rc;
-        CUDA_TRY(cudaStreamSynchronize(st));  // cen, nrm are locals
-        if (getenv("CGE_B200_PHASES")) fprintf(stderr, "[cge_b200] recompute regime: row-norm/dot form\n");
+    h->rc_dot = !stored && want != CGE_B200_REGIME_RECOMPUTE_DIFF &&
+                !(rc_form && std::strcmp(rc_form, "diff") == 0);
+    h->regime_reported = stored ? CGE_B200_REGIME_STORED
+                         : !h->rc_dot ? CGE_B200_REGIME_RECOMPUTE_DIFF
+                         : want == CGE_B200_REGIME_RECOMPUTE_DOT ? CGE_B200_REGIME_RECOMPUTE_DOT
+                                                                 : CGE_B200_REGIME_RECOMPUTE;
+    if (stored || !h->rc_dot) {  // the tile table: stored sweeps, k_build_dist
+        std::vector<int2> tij = make_tile_table(h->nb);
+        if ((rc = upload_vec(h->tile_ij, tij.data(), tij.size() * sizeof(int2), st))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));  // tij is a local
     }
-    const size_t part_bytes = (size_t)h->nb * (size_t)np * 8;
+    size_t part_rows = (size_t)h->nb;
+    if (!stored) {
+        // ---- super-tiles (cge_rc.cuh): the smallest super-block that keeps the partial slots
+        // under 2 GiB, at most RC_MAX_SB; CGE_B200_RC_SB overrides (tests) ----
+        int sb = 1;
+        while (sb < RC_MAX_SB && (size_t)((h->nb + sb - 1) / sb) * (size_t)np * 8 * (h->directed ? 2 : 1) >
+                                     ((size_t)2 << 30))
+            sb *= 2;
+        if (const char *e = getenv("CGE_B200_RC_SB")) {
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4 || v == 8) sb = v;
+        }
+        h->sb = sb;
+        h->nsb = (h->nb + sb - 1) / sb;
+        h->n_st = h->nsb * (h->nsb + 1) / 2;
+        std::vector<int2> stij;
+        stij.reserve((size_t)h->n_st);
+        std::vector<int64_t> pre((size_t)h->n_st + 1, 0);  // tiles before super-tile s
+        auto side = [&](int64_t I) { return std::min<int64_t>(sb, h->nb - I * sb); };
+        for (int64_t I = 0; I < h->nsb; ++I)
+            for (int64_t J = I; J < h->nsb; ++J) {
+                const int64_t r = side(I), c = side(J);
+                pre[stij.size() + 1] = pre[stij.size()] + (I == J ? r * (r + 1) / 2 : r * c);
+                stij.push_back(make_int2((int)I, (int)J));
+            }
+        // contiguous shares of near-equal tile counts
+        auto cut = [&](int r) {
+            const int64_t target = pre[(size_t)h->n_st] * r / h->n_ranks;
+            return (int64_t)(std::lower_bound(pre.begin(), pre.end(), target) - pre.begin());
+        };
+        h->st_begin = h->rank == 0 ? 0 : cut(h->rank);
+        h->st_end = h->rank == h->n_ranks - 1 ? h->n_st : cut(h->rank + 1);
+        h->srow_begin = h->st_end > h->st_begin ? stij[(size_t)h->st_begin].x : 0;
+        h->srow_end = h->st_end > h->st_begin ? stij[(size_t)h->st_end - 1].x : -1;
+        if ((rc = upload_vec(h->st_ij, stij.data(), stij.size() * sizeof(int2), st))) return rc;
+        part_rows = (size_t)h->nsb;
+        // ---- operand image and row norms ----
+        std::vector<double> mean((size_t)dp, 0.0);
+        if (h->rc_dot) {
+            for (int64_t r = 0; r < n; ++r)
+                for (int64_t c = 0; c < p->d; ++c) mean[(size_t)c] += emb[(size_t)(r * dp + c)];
+            for (int64_t c = 0; c < p->d; ++c) mean[(size_t)c] /= (double)n;
+        }
+        if ((rc = upload_vec(h->rc_mean, mean.data(), mean.size() * 8, st))) return rc;
+        if ((rc = h->opT.ensure((size_t)np * (size_t)dp * 8))) return rc;
+        if ((rc = h->nrm.ensure((size_t)np * 8))) return rc;
+        launch_rc_pack(h->emb.as<double>(), h->rc_mean.as<double>(), (int)n, (int)np, (int)dp,
+                       h->opT.as<double>(), h->rc_dot ? h->nrm.as<double>() : nullptr, st);
+        CUDA_TRY(cudaStreamSynchronize(st));  // stij, mean are locals
+        CUDA_TRY(cudaGetLastError());
+        if (trace)
+            fprintf(stderr, "[cge_b200] recompute regime: %s form, super-block %d (%lld super-tiles, %lld..%lld here)\n",
+                    h->rc_dot ? "row-norm/dot" : "difference", sb, (long long)h->n_st,
+                    (long long)h->st_begin, (long long)h->st_end);
+    }
+    const size_t part_bytes = part_rows * (size_t)np * 8;
     if ((rc = h->partA.ensure(part_bytes))) return rc;
     if (h->directed && (rc = h->partB.ensure(part_bytes))) return rc;
     for (DevBuf *b : {&h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->qdiag})
@@ -1040,21 +1125,21 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     S.n = h->n;
     S.n_pairs = h->n * (h->n + 1) / 2;
     S.n_ranks = h->n_ranks;
-    // the persistent kernel cannot call NCCL between passes: multi-rank runs use the host loop
-    const bool can_p2p = h->n_ranks > 1 && h->p2p_ready && h->np <= h->xcap &&
-                         h->regime == CGE_B200_REGIME_STORED;
+    // the persistent kernel cannot call NCCL between passes: multi-rank runs without the peer
+    // exchange use the host loop.  Ranks that are threads of this process have no NCCL communicator
+    // at all (their small reductions go through the LocalGroup), so they always run persistent.
+    const bool can_p2p = h->n_ranks > 1 && h->p2p_ready && h->np <= h->xcap;
     if (h->group && !can_p2p)
-        return fail(CGE_B200_ERR_STATE,
-                    "in-process multi-GPU needs the stored regime and the peer exchange");
+        return fail(CGE_B200_ERR_STATE, "in-process multi-GPU needs the peer exchange");
     const int driver =
-        h->n_ranks > 1 ? ((can_p2p && h->driver != CGE_B200_DRIVER_HOSTLOOP)
+        h->n_ranks > 1 ? ((can_p2p && (h->driver != CGE_B200_DRIVER_HOSTLOOP || h->group))
                               ? CGE_B200_DRIVER_PERSISTENT
                               : CGE_B200_DRIVER_HOSTLOOP)
         : h->driver == CGE_B200_DRIVER_AUTO
             ? CGE_B200_DRIVER_PERSISTENT  // measured: 65.3 us/pass vs 72.2 for the TMA ring (r01)
             : h->driver;
     S.driver = driver;
-    S.regime = h->rc_dot ? CGE_B200_REGIME_RECOMPUTE_DOT : h->regime;
+    S.regime = h->regime_reported;
     const bool stored = h->regime == CGE_B200_REGIME_STORED;
     // small problems (fewer tiles than resident CTAs): one run-time-exponent kernel for the whole
     // alpha grid instead of one instantiation per alpha (first-use load time, see powm_any)
@@ -1075,11 +1160,13 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     h->ev_is_b.clear();
     const int n = (int)h->n, np = (int)h->np, nb = (int)h->nb, dp = (int)h->dp, k = (int)h->k;
     const long long tb = h->tile_begin, te = h->tile_end;
-    const int local_tiles = (int)(te - tb);
-    const int grid = std::max(1, std::min(local_tiles, 2 * h->sm_count));
+    // work units of this rank: tiles (stored regime) or super-tiles (recompute regime, one CTA per SM)
+    const int local_tiles = stored ? (int)(te - tb) : (int)(h->st_end - h->st_begin);
+    const int grid = std::max(1, std::min(local_tiles, (stored ? 2 : 1) * h->sm_count));
+    const int build_tiles = (int)(te - tb), build_grid = std::max(1, std::min(build_tiles, 2 * h->sm_count));
     S.n_tiles = (int)h->n_tiles;
     S.grid = grid;
-    S.matrix_bytes = stored ? (int64_t)local_tiles * TILE_ELEMS * 8 : 0;
+    S.matrix_bytes = stored ? (int64_t)build_tiles * TILE_ELEMS * 8 : 0;
     // three phase markers come from the handle's event pool (no create/destroy per run, nothing
     // to leak on the error paths below)
     cudaEvent_t ev0 = h->next_event(), ev1 = h->next_event(), ev2 = h->next_event();
@@ -1096,37 +1183,51 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         init[3] = 0ull;
         CUDA_TRY(cudaMemcpyAsync(lohi, init, sizeof(init), cudaMemcpyHostToDevice, st));
     }
-    if (local_tiles > 0) {
-        if (stored)
-            k_build_dist<true><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
-                                                          h->dist.as<double>(), n,
-                                                          h->tile_ij.as<int2>(), tb, te,
-                                                          h->q.as<double>(), lohi);
-        else if (h->rc_dot) {  // ... in the arithmetic the passes will use
-            SweepArgs E = {};
-            E.tile_ij = h->tile_ij.as<int2>();
-            E.tile_begin = tb;
-            E.tile_end = te;
-            E.n = n;
-            E.np = np;
-            E.dp = dp;
-            E.emb = h->emb.as<double>();
-            E.emb_c = h->emb_c.as<double>();
-            E.nrm = h->nrm.as<double>();
-            E.diag = h->dist.as<double>();
-            launch_extrema_rc(grid, st, E, lohi);
-        } else  // recompute regime: only the extrema are needed up front
-            k_build_dist<false><<<grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
-                                                           h->dist.as<double>(), n,
-                                                           h->tile_ij.as<int2>(), tb, te, nullptr,
-                                                           lohi);
+    RcArgs A = {};  // the stored-regime kernels take its SweepArgs base
+    A.tile_ij = h->tile_ij.as<int2>();
+    A.tile_begin = tb;
+    A.tile_end = te;
+    A.nb = nb; A.np = np; A.n = n; A.k = k;
+    A.emb = h->emb.as<double>();
+    A.nrm = h->rc_dot ? h->nrm.as<double>() : nullptr;
+    A.diag = h->dist.as<double>();
+    A.lohi = lohi;
+    A.dp = dp;
+    A.m = 1;
+    A.st_ij = h->st_ij.as<int2>();
+    A.st_begin = h->st_begin;
+    A.st_end = h->st_end;
+    A.sb = h->sb;
+    A.nsb = (int)h->nsb;
+    A.srow_begin = h->srow_begin;
+    A.srow_end = h->srow_end;
+    A.nchunk = dp / RC_DK;
+    A.opT = h->opT.as<double>();
+    if (stored) {
+        if (build_tiles > 0) {
+            k_build_dist<true><<<build_grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
+                                                                h->dist.as<double>(), n,
+                                                                h->tile_ij.as<int2>(), tb, te,
+                                                                h->q.as<double>(), lohi);
+            ++h->launches;
+        }
+    } else if (h->rc_dot) {  // recompute regime: only the extrema are needed up front, in the
+        if (local_tiles > 0) {  // arithmetic the passes will use
+            launch_extrema_rc(grid, st, A, lohi);
+            ++h->launches;
+        }
+    } else if (build_tiles > 0) {  // difference form: the FMA chain of k_build_dist is the passes'
+        k_build_dist<false><<<build_grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
+                                                             h->dist.as<double>(), n,
+                                                             h->tile_ij.as<int2>(), tb, te, nullptr,
+                                                             lohi);
         ++h->launches;
     }
     if (h->n_ranks > 1)
         if (int rc = reduce_extrema_across_ranks(h, lohi, st)) return rc;
-    if (local_tiles > 0 && stored) {
+    if (build_tiles > 0 && stored) {
         k_transform<<<4 * h->sm_count, 256, 0, st>>>(h->q.as<double>(),
-                                                     (size_t)local_tiles * TILE_ELEMS, lohi);
+                                                     (size_t)build_tiles * TILE_ELEMS, lohi);
         ++h->launches;
     }
     k_qdiag<<<(n + 255) / 256, 256, 0, st>>>(h->dist.as<double>(), n, lohi, h->qdiag.as<double>());
@@ -1141,10 +1242,12 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         const unsigned long long *lh = h->landmark ? lohi + 2 : lohi;
         const int blocks = (int)((SK + 255) / 256);
         if (h->rc_dot && !h->landmark) {  // the sampled pairs get the bits the passes use
-            launch_sample_q_dot(h->emb_c.as<double>(), h->nrm.as<double>(), e, dp, h->s_pda.as<int>(),
-                                h->s_pdb.as<int>(), dg, lh, SK, h->s_pq.as<double>(), st);
-            launch_sample_q_dot(h->emb_c.as<double>(), h->nrm.as<double>(), e, dp, h->s_nda.as<int>(),
-                                h->s_ndb.as<int>(), dg, lh, SK, h->s_nq.as<double>(), st);
+            launch_sample_q_dot(h->opT.as<double>(), dp / RC_DK, h->nrm.as<double>(), e, dp,
+                                h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh, SK,
+                                h->s_pq.as<double>(), st);
+            launch_sample_q_dot(h->opT.as<double>(), dp / RC_DK, h->nrm.as<double>(), e, dp,
+                                h->s_nda.as<int>(), h->s_ndb.as<int>(), dg, lh, SK,
+                                h->s_nq.as<double>(), st);
         } else {
             k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh,
                                                h->landmark, SK, h->s_pq.as<double>());
@@ -1157,16 +1260,13 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     CUDA_TRY(cudaMemcpyAsync(h->Ta.p, h->T0a.p, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
     if (h->directed)
         CUDA_TRY(cudaMemcpyAsync(h->Tb.p, h->T0b.p, (size_t)np * 8, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(cudaMemsetAsync(h->partA.p, 0, (size_t)nb * np * 8, st));
-    if (h->directed) CUDA_TRY(cudaMemsetAsync(h->partB.p, 0, (size_t)nb * np * 8, st));
+    const size_t part_bytes = (size_t)(stored ? nb : (int)h->nsb) * np * 8;
+    CUDA_TRY(cudaMemsetAsync(h->partA.p, 0, part_bytes, st));
+    if (h->directed) CUDA_TRY(cudaMemsetAsync(h->partB.p, 0, part_bytes, st));
     CUDA_TRY(cudaMemsetAsync(h->slots.p, 0, 64, st));
     CUDA_TRY(cudaEventRecord(ev1, st));
 
-    SweepArgs A;
     A.q = h->q.as<double>();
-    A.tile_ij = h->tile_ij.as<int2>();
-    A.tile_begin = tb;
-    A.tile_end = te;
     {   // tile rows covered by [tb, te): row bi starts at tile bi*nb - bi(bi-1)/2
         auto row_of = [&](long long t) {
             int bi = 0;
@@ -1176,7 +1276,6 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         A.row_begin = te > tb ? row_of(tb) : 0;
         A.row_end = te > tb ? row_of(te - 1) : -1;
     }
-    A.nb = nb; A.np = np; A.n = n; A.k = k;
     A.Ta = h->Ta.as<double>();
     A.Tb = h->Tb.as<double>();
     A.partA = h->partA.as<double>();
@@ -1213,13 +1312,6 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         A.phase_ns = h->slots.as<unsigned long long>() + 8;  // bytes 64..127 of the slots buffer
         CUDA_TRY(cudaMemsetAsync(A.phase_ns, 0, 64, st));
     }
-    A.emb = h->emb.as<double>();
-    A.emb_c = h->rc_dot ? h->emb_c.as<double>() : nullptr;
-    A.nrm = h->rc_dot ? h->nrm.as<double>() : nullptr;
-    A.diag = h->dist.as<double>();
-    A.lohi = lohi;
-    A.dp = dp;
-    A.m = 1;
 
     SampleSide sp, sn;
     if (h->K > 0) {
@@ -1267,7 +1359,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             int bps = 0;
             CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, threads, smem));
             if (bps < 1) return fail(CGE_B200_ERR_CUDA, "fixed-point kernel does not fit on an SM");
-            const int want = std::max(local_tiles, (n + 31) / 32);
+            const int want = stored ? std::max(local_tiles, (n + 31) / 32)
+                                    : std::max(local_tiles, 1);  // recompute: never more CTAs than units
             const int cgrid = std::max(1, std::min(want, bps * h->sm_count));
             A.eps0 = eps;
             A.pass_base = h->pass_total;
@@ -1285,18 +1378,19 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         while (driver == CGE_B200_DRIVER_HOSTLOOP && diff > delta) {  // :151 / :436
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
-                if (!stored) launch_tiles_rc(h->directed ? 1 : 0, grid, st, A);
+                if (!stored) launch_tiles_rc(h->directed ? 1 : 0, grid, st, A, h->rc_dot);
                 else if (small) launch_tiles_rt(h->directed ? 1 : 0, grid, st, A);
                 else launch_tiles(m, h->directed ? 1 : 0, grid, st, A);
                 cudaEventRecord(h->next_event(), st);
                 h->ev_is_b.push_back(0);
                 ++h->launches;
             }
-            k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A, A.partA, h->sraw_a.as<double>());
+            if (stored) k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A, A.partA, h->sraw_a.as<double>());
+            else launch_reduce_part_rc(A, A.partA, h->sraw_a.as<double>(), st);
             ++h->launches;
             if (h->directed) {
-                k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A, A.partB,
-                                                                  h->sraw_b.as<double>());
+                if (stored) k_reduce_part<<<(n + 31) / 32, NTHREADS, 0, st>>>(A, A.partB, h->sraw_b.as<double>());
+                else launch_reduce_part_rc(A, A.partB, h->sraw_b.as<double>(), st);
                 ++h->launches;
             }
             if (h->n_ranks > 1) {
@@ -1359,7 +1453,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
-                if (!stored) launch_tiles_rc(h->directed ? 3 : 2, grid, st, A);
+                if (!stored) launch_tiles_rc(h->directed ? 3 : 2, grid, st, A, h->rc_dot);
                 else if (small) launch_tiles_rt(h->directed ? 3 : 2, grid, st, A);
                 else launch_tiles(m, h->directed ? 3 : 2, grid, st, A);
                 cudaEventRecord(h->next_event(), st);
@@ -1527,7 +1621,7 @@ void cge_b200_destroy(cge_b200_handle *h) {
     for (DevBuf *b :
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
-          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->emb_c, &h->nrm, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
+          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->st_ij, &h->opT, &h->nrm, &h->rc_mean, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
           &h->diam_list, &h->diam_ctr, &h->diam_mean, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
           &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})
@@ -1717,6 +1811,11 @@ int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles) {
             h->xpeer[r] = ptr;
         }
     }
+    // a fresh exchange: pass numbers restart at 1, so no record of an earlier one may survive.
+    // Peers write into this buffer only from inside run(), which every rank enters after its own
+    // import (the caller's collective upload / barrier comes in between).
+    CUDA_TRY(cudaMemset(h->xbuf, 0, (size_t)2 * h->n_ranks * 2 * (size_t)h->xcap * 16));
+    CUDA_TRY(cudaDeviceSynchronize());
     h->pass_total = 0;
     h->p2p_ready = true;
     return 0;
@@ -1727,6 +1826,14 @@ int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops) {
     CUDA_TRY(cudaSetDevice(h->device));
     *tflops = measure_fp64_peak_tflops(h->sm_count, h->stream);
     if (*tflops <= 0.0) return fail(CGE_B200_ERR_CUDA, "FP64 peak measurement failed");
+    return 0;
+}
+
+int cge_b200_measure_fp64_pipes(cge_b200_handle *h, double out[8]) {
+    if (!h || !out) return fail(CGE_B200_ERR_ARG, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (measure_fp64_pipes(h->sm_count, h->stream, out) != 0)
+        return fail(CGE_B200_ERR_CUDA, "FP64 pipe measurement failed");
     return 0;
 }
 

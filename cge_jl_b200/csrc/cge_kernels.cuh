@@ -723,18 +723,11 @@ cudaError_t launch_diameter_filter(const DiamArgs &a, int grid, cudaStream_t st)
 void launch_select_candidates(const float *tile_max, long long n_tiles, const unsigned *gmax_bits,
                               const unsigned *rmax_bits, float rel, int *list, int cap, int *count,
                               cudaStream_t st);
-// recompute regime (cge_recompute.cu): kind as in launch_tiles, exponent taken from a.m
-void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const SweepArgs &a);
-const void *fp_kernel_rc(int directed, int dot);
-void launch_extrema_rc(int grid, cudaStream_t stream, const SweepArgs &a, unsigned long long *lohi);
-void launch_sample_q_dot(const double *emb_c, const double *nrm, const double *emb, int dp,
-                         const int *ia, const int *ib, const double *diag,
-                         const unsigned long long *lohi, long long count, double *out,
-                         cudaStream_t stream);
-size_t rc_smem_bytes();  // dynamic shared memory of every recompute kernel
+// recompute regime: see cge_rc.cuh
 void launch_selftest_math(long long n, unsigned long long seed, unsigned long long *out, int grid,
                           cudaStream_t st);
 double measure_fp64_peak_tflops(int sm_count, cudaStream_t st);
+int measure_fp64_pipes(int sm_count, cudaStream_t st, double *out);  // cge_microbench.cu
 // device sampler of non-edges (cge_sampler.cu)
 void launch_edge_set_insert(const long long *src, const long long *dst, long long m, long long n,
                             int index_base, int directed, unsigned long long *table,

@@ -190,6 +190,13 @@ class Scorer:
         _check(self._lib.cge_b200_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
 
+    def fp64_pipes_tflops(self):
+        """``cge_b200_measure_fp64_pipes``: DFMA / DMMA throughput of the device, see the header."""
+        out = np.zeros(8)
+        _check(self._lib.cge_b200_measure_fp64_pipes(self._h, _pd(out)))
+        return dict(zip(("dfma", "dmma_m8n8k4", "dmma_m16n8k16", "mix_m8n8k4_dmma", "mix_m8n8k4_dfma",
+                         "mix_m16n8k16_dmma", "mix_m16n8k16_dfma", "dmma_m16n8k8"), out.tolist()))
+
     def sample_non_edges(self, edges, n, K, n_sets=1, seed=0, directed=False, index_base=1,
                          return_draws=False):
         """``cge_b200_sample_non_edges``: ``(neg_i, neg_j)`` of shape ``(n_sets, K)``, uniform over

@@ -51,14 +51,18 @@ enum {
 
 /* where the pair matrix lives */
 enum {
-    CGE_B200_REGIME_AUTO = 0,         /* stored when it fits in free HBM, else recompute */
-    CGE_B200_REGIME_STORED = 1,       /* q = (1-D)^(1/4) kept in HBM: 8 B per pair and pass, HBM bound */
-    CGE_B200_REGIME_RECOMPUTE = 2,    /* distances re-derived from the embedding every pass: FP64 bound */
-    CGE_B200_REGIME_RECOMPUTE_DOT = 3 /* the same with d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding
-                                         (one FMA per dimension and pair; pairs under cancellation use
-                                         the difference form; extrema and sampled pairs share the
-                                         arithmetic).  Opt-in, never chosen by AUTO; also selected by
-                                         CGE_B200_RC_FORM=dot when the regime resolves to RECOMPUTE */
+    CGE_B200_REGIME_AUTO = 0,          /* stored when it fits in free HBM, else recompute */
+    CGE_B200_REGIME_STORED = 1,        /* q = (1-D)^(1/4) kept in HBM: 8 B per pair and pass, HBM bound */
+    CGE_B200_REGIME_RECOMPUTE = 2,     /* distances re-derived from the embedding every pass (FP64 bound),
+                                          from d^2 = n_i + n_j - 2 x_i.x_j on the centred embedding: one
+                                          FMA per dimension and pair; pairs under cancellation use the
+                                          difference form; extrema and sampled pairs share the arithmetic */
+    CGE_B200_REGIME_RECOMPUTE_DOT = 3, /* the same (the name of round 1, when it was opt-in); reported back
+                                          as 3 when asked for as 3 */
+    CGE_B200_REGIME_RECOMPUTE_DIFF = 4 /* recompute with the reference's difference form sum (x_i - x_j)^2
+                                          (auxilary.jl:14-20): two FP64 instructions per dimension and
+                                          pair; the cross-check of the default.  CGE_B200_RC_FORM=diff
+                                          selects it whenever the regime resolves to recompute */
 };
 
 /*
@@ -184,6 +188,12 @@ int cge_b200_p2p_import(cge_b200_handle *h, const void *all_handles);
 /* Measured FP64 FMA throughput of the handle's device in TFLOP/s (2 flop per FMA): the roofline
  * denominator of the recompute regime, which MEASURED_PEAKS.json does not provide. */
 int cge_b200_measure_fp64_peak(cge_b200_handle *h, double *tflops);
+
+/* The same for every way this device can issue FP64 multiply-adds (cge_microbench.cu): out[0] DFMA,
+ * out[1] mma.sync m8n8k4 (DMMA), out[2] m16n8k16, out[3]/out[4] DMMA and DFMA shares of a 4:1 mix
+ * (do the two share a pipe?), out[5]/out[6] the same for m16n8k16 with an 8:1 mix, out[7] m16n8k8;
+ * all in TFLOP/s.  Design evidence for the Gram step of the recompute regime. */
+int cge_b200_measure_fp64_pipes(cge_b200_handle *h, double out[8]);
 
 /* SURVEY.md 8(f) F1 -- the negative pairs of the local score drawn on the device.  Replaces the
  * reference's NE construction (all pairs minus the edge Set, divergence.jl:121-137 / 405-421: n^2/2

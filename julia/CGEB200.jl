@@ -84,7 +84,7 @@ function sample_non_edges_device(adj_edges::Array{Int,2}, n::Int, K::Int, n_sets
                         (Ptr{Cvoid}, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Int32, Int32, Int64, Int64,
                          UInt64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                         h[], n, m, src, dst, 1, directed ? 1 : 0, K, n_sets,
-                        seed == -1 ? rand(UInt64) : UInt64(seed), neg_i, neg_j, C_NULL))
+                        seed == -1 ? rand(UInt64) : reinterpret(UInt64, Int64(seed)), neg_i, neg_j, C_NULL))
         end
     finally
         ccall((:cge_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])

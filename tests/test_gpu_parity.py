@@ -139,20 +139,39 @@ def test_synthetic_multi_tile(scorer, directed, n, k, d, driver):
     assert_parity(out, stats, ref, tr)
 
 
+@pytest.mark.parametrize("regime", [2, 4], ids=["dot", "diff"])
 @pytest.mark.parametrize("driver", [1, 2], ids=["hostloop", "persistent"])
 @pytest.mark.parametrize("directed,n,k,d", [(False, 115, 0, 0), (True, 115, 0, 0),
                                             (False, 700, 5, 20), (True, 520, 7, 33)])
-def test_recompute_regime(scorer, directed, n, k, d, driver):
+def test_recompute_regime(scorer, directed, n, k, d, driver, regime):
     """No stored matrix: distances are re-derived from the embedding in every pass (north_star
-    kernel (a)); same parity bars against the oracle as the stored regime."""
+    kernel (a)), from the row norms and dot products of the centred embedding (regime 2, the
+    default) or in the reference's difference form (regime 4); same parity bars against the oracle
+    as the stored regime."""
     if k == 0:
         edges, ew, vw, comm, emb = load_fixture("test115_weighted.npz" if directed else "test115.npz")
     else:
         edges, ew, vw, comm, emb = planted_partition(n, k, d, seed=n + k, directed=directed,
                                                      weighted=True)
     out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
-                                   driver=driver, regime=2)
+                                   driver=driver, regime=regime)
     assert stats.matrix_bytes == 0
+    assert_parity(out, stats, ref, tr)
+
+
+@pytest.mark.parametrize("sb", [2, 4, 8])
+@pytest.mark.parametrize("directed,driver", [(False, 2), (True, 2), (False, 1)])
+def test_recompute_super_tiles(scorer, directed, driver, sb, monkeypatch):
+    """Super-tiles of sb x sb tiles (what 10^5..10^6 vertices use to keep the partial-sum slots
+    small) forced on a 1 100-vertex graph: 9 tile rows make whole, ragged and diagonal super-tiles;
+    d = 70 gives 5 staging chunks per tile, more than the 4 ring stages."""
+    monkeypatch.setenv("CGE_B200_RC_SB", str(sb))
+    n = 1100
+    edges, ew, vw, comm, emb = planted_partition(n, 6, 70, seed=sb + 5 * directed, directed=directed,
+                                                 weighted=True)
+    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
+                                   driver=driver, regime=2)
+    assert stats.matrix_bytes == 0 and stats.regime == 2
     assert_parity(out, stats, ref, tr)
 
 
@@ -174,7 +193,8 @@ def test_recompute_row_norm_dot_form(scorer, directed, n, k, d):
 
 def test_recompute_branch_free_math_matches_ieee(scorer):
     """The recompute epilogue's branch-free sqrt / divide return the bits of the IEEE operations
-    (2^26 pseudo-random operands in the epilogue's ranges, zeros and denormals included)."""
+    (2^26 pseudo-random operands in the epilogue's ranges, zeros included; operands under 2^-943
+    must come back as exactly 0, the documented select)."""
     assert scorer.selftest_math(1 << 26, seed=2024) == (0, 0)
 
 
@@ -186,6 +206,24 @@ def test_recompute_regime_landmarks_with_diagonal(scorer):
     out, stats, ref, tr = run_pair(scorer, False, ledges, lw, lcomm, lemb, dii, lweight,
                                    lm_args=(vw, v2l, edges, ew, emb), regime=2)
     assert_parity(out, stats, ref, tr)
+
+
+def test_sample_sets_must_cover_the_alpha_grid(scorer):
+    """n_sets is 1 (seeded: the same pairs for every alpha) or one set per evaluated alpha; anything
+    in between would index past the sample buffers from alpha n_sets + 1 on and is refused."""
+    edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    n = vw.shape[0]
+    samples = dv.draw_samples(edges, ew, n, 300, -1, False, True)  # 40 sets
+    two = tuple(a[:2] for a in samples)
+    p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False, False,
+                              two)
+    with pytest.raises(RuntimeError, match="n_sets"):
+        scorer.upload(p, keep)
+    p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False, False,
+                              two, max_alphas=2)  # two sets do cover a two-alpha run
+    scorer.upload(p, keep)
+    out, st = scorer.run()
+    assert st.n_alpha_run == 2 and np.all(np.isfinite(out))
 
 
 def test_star_graph_early_exit(scorer):

@@ -1,7 +1,9 @@
-"""GPU (>= 2 devices): the tile-sharded exact mode.  Two ranks (one process per GPU) own halves
-of the tile sequence and all-reduce the partial degree sums every pass over NCCL; the result
-must match the single-GPU run (identical pass counts and best alphas, scores within 1e-9) and
-the CPU oracle.  Skipped on a one-GPU box; run with `gpurun --gpus 2`."""
+"""GPU (>= 2 devices): the sharded exact mode.  2, 4 or 8 ranks (one process per GPU, as many as the
+box has) own contiguous shares of the tile sequence (stored regime) or of the super-tile sequence
+(recompute regime) and exchange the partial degree sums every pass -- over NCCL from the host
+loop, or over NVLink peer memory inside the persistent kernel; the result must match the
+single-GPU run (identical pass counts and best alphas, scores within 1e-9) and the CPU oracle.
+Cases that need more GPUs than the box has are skipped; run with `gpurun --gpus N`."""
 import os
 import socket
 
@@ -26,10 +28,12 @@ def _problem(directed):
     return n, edges, ew, vw, comm, emb
 
 
-def _worker(rank, world, port, directed, p2p, q):
+def _worker(rank, world, port, directed, p2p, regime, q):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if regime == 2:
+        os.environ["CGE_B200_RC_SB"] = "2"  # super-tiles of 2 x 2 tiles: 21 work units over the ranks
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world,
                             device_id=torch.device("cuda", rank))
@@ -45,22 +49,34 @@ def _worker(rank, world, port, directed, p2p, q):
         dist.all_gather_object(handles, sc.p2p_export(n))
         sc.p2p_import(handles)
     p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False,
-                              directed, samples)
+                              directed, samples, 0, 0, regime)
     sc.upload(p, keep)
     out, st = sc.run()
     dist.barrier()
     if rank == 0:
-        q.put((out, list(st.iters), list(st.div), list(st.auc), int(st.n_ranks), int(st.driver)))
+        q.put((out, list(st.iters), list(st.div), list(st.auc), int(st.n_ranks), int(st.driver),
+               int(st.regime)))
     sc.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("p2p", [False, True], ids=["nccl-hostloop", "nvlink-persistent"])
-@pytest.mark.parametrize("directed", [False, True])
-def test_two_gpu_matches_one_gpu_and_oracle(directed, p2p):
+CASES = [(2, False, False, 1), (2, True, False, 1), (2, False, True, 1), (2, True, True, 1),
+         (2, False, True, 2), (2, True, True, 2), (2, False, False, 2),
+         (4, False, True, 1), (4, True, True, 2), (8, False, True, 1), (8, False, True, 2),
+         (8, True, True, 1)]
+
+
+@pytest.mark.parametrize("world,directed,p2p,regime", CASES,
+                         ids=[f"{w}gpu-{'dir' if d else 'undir'}-{'nvlink' if p else 'nccl'}-"
+                              f"{'stored' if r == 1 else 'recompute'}" for w, d, p, r in CASES])
+def test_sharded_matches_one_gpu_and_oracle(world, directed, p2p, regime):
+    """The tile (stored) or super-tile (recompute) sequence sharded over `world` ranks, per-pass
+    exchange through NCCL from the host loop or over NVLink peer memory inside the persistent
+    kernel: identical pass counts and best alphas, scores within 1e-9 of the single-GPU run and of
+    the oracle."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
     import oracle
@@ -70,14 +86,15 @@ def test_two_gpu_matches_one_gpu_and_oracle(directed, p2p):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, directed, p2p, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, directed, p2p, regime, q))
+             for r in range(world)]
     for p in procs:
         p.start()
-    out2, iters2, div2, auc2, n_ranks, driver = q.get(timeout=300)
+    out2, iters2, div2, auc2, n_ranks, driver, reg = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert n_ranks == 2 and driver == (2 if p2p else 1)
+    assert n_ranks == world and driver == (2 if p2p else 1) and reg == regime
     n, edges, ew, vw, comm, emb = _problem(directed)
     samples = dv.draw_samples(edges, ew, n, 2000, 42, directed, True)
     f = dv.wGCL_directed if directed else dv.wGCL
@@ -95,10 +112,14 @@ def test_two_gpu_matches_one_gpu_and_oracle(directed, p2p):
     assert_parity(out2, St, ref, tr)
 
 
+@pytest.mark.parametrize("regime,driver", [(1, 0), (2, 0), (1, 1)],
+                         ids=["stored", "recompute", "stored-hostloop-asked"])
 @pytest.mark.parametrize("directed", [False, True])
-def test_single_process_two_gpus(directed):
+def test_single_process_two_gpus(directed, regime, driver):
     """cge_b200_score_multi: the ranks are threads of one process (the Julia ccall case); peers
-    are reached by plain peer access, extrema and B are reduced on the host."""
+    are reached by plain peer access, extrema and B are reduced on the host.  There is no NCCL
+    communicator on this path, so a request for the host-loop driver still runs the persistent
+    kernel (it used to dereference the missing communicator)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -108,9 +129,9 @@ def test_single_process_two_gpus(directed):
     n, edges, ew, vw, comm, emb = _problem(directed)
     samples = dv.draw_samples(edges, ew, n, 2000, 42, directed, True)
     p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False,
-                              directed, samples)
+                              directed, samples, 0, driver, regime)
     out2, st2 = dv.score_multi(p, 2)
-    assert st2.n_ranks == 2 and st2.driver == 2
+    assert st2.n_ranks == 2 and st2.driver == 2 and st2.regime == regime
     f = dv.wGCL_directed if directed else dv.wGCL
     out1, st1 = f(edges, ew, comm, emb, np.zeros(n), vw, *empty_landmark_args(), False, 42, 2000,
                   False, samples=samples, return_stats=True)
