@@ -542,7 +542,10 @@ struct cge_b200_handle {
     DevBuf q, tile_ij, tile_ij_full, emb, emb_full, dist, w, w2, T0a, T0b, Ta, Tb, Sa, Sb, sraw_a,
         sraw_b, partA, partB, comm, B, qdiag, lohi, slots, auc_out, fpres;
     // recompute regime: super-tile table, operand image (centred for the row-norm / dot form), row norms
-    DevBuf st_ij, opT, nrm, rc_mean;
+    DevBuf st_ij, opT, nrm, rc_mean, st_pre, qst;
+    std::vector<int64_t> st_pre_host;    // tiles before super-tile s in the global sequence
+    int64_t st_store_end = 0;            // super-tiles [st_begin, st_store_end) keep their q tiles in HBM
+    bool store_auto = false;             // regime chosen by AUTO: keep as much of the matrix as fits
     bool rc_dot = false;
     int regime_reported = CGE_B200_REGIME_STORED;
     int sb = 1;                          // tiles per super-block side
@@ -869,6 +872,10 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         h->srow_begin = h->st_end > h->st_begin ? stij[(size_t)h->st_begin].x : 0;
         h->srow_end = h->st_end > h->st_begin ? stij[(size_t)h->st_end - 1].x : -1;
         if ((rc = upload_vec(h->st_ij, stij.data(), stij.size() * sizeof(int2), st))) return rc;
+        if ((rc = upload_vec(h->st_pre, pre.data(), pre.size() * 8, st))) return rc;
+        h->st_pre_host = pre;
+        h->st_store_end = h->st_begin;
+        h->store_auto = want == CGE_B200_REGIME_AUTO;
         part_rows = (size_t)h->nsb;
         // ---- operand image and row norms ----
         std::vector<double> mean((size_t)dp, 0.0);
@@ -1010,6 +1017,35 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
         if ((rc = h->s_nq.ensure((size_t)S * 8))) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(st));
+    if (!stored) {
+        // ---- "store what fits": with everything else allocated, the leading super-tiles of this rank
+        // keep their q tiles in what is left of HBM (minus 4 GB + 3 % head-room) and are read in every
+        // pass instead of being recomputed.  Only when the regime was left to AUTO (an explicit
+        // recompute request recomputes everything), or with CGE_B200_STORE_MB = the budget in MB ----
+        size_t budget = 0;
+        if (const char *e = getenv("CGE_B200_STORE_MB")) {
+            budget = (size_t)std::max(0.0, atof(e)) << 20;
+        } else if (h->store_auto) {
+            size_t free_b = 0, total_b = 0;
+            CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+            const size_t avail = free_b + h->qst.cap, reserve = ((size_t)4 << 30) + total_b / 32;
+            budget = avail > reserve ? avail - reserve : 0;
+        }
+        const int64_t tiles_fit = (int64_t)(budget / ((size_t)TILE_ELEMS * 8));
+        const std::vector<int64_t> &pre = h->st_pre_host;
+        int64_t e = h->st_begin;
+        while (e < h->st_end && pre[(size_t)e + 1] - pre[(size_t)h->st_begin] <= tiles_fit) ++e;
+        h->st_store_end = e;
+        const size_t bytes = (size_t)(pre[(size_t)e] - pre[(size_t)h->st_begin]) * TILE_ELEMS * 8;
+        if (bytes) {
+            if ((rc = h->qst.ensure(bytes))) return rc;
+        } else {
+            h->qst.release();
+        }
+        if (trace)
+            fprintf(stderr, "[cge_b200] store what fits: %lld of %lld super-tiles of this rank (%.2f GB)\n",
+                    (long long)(e - h->st_begin), (long long)(h->st_end - h->st_begin), bytes / 1e9);
+    }
     h->uploaded = true;
     lap("samples");
     h->ms_upload =
@@ -1166,7 +1202,11 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     const int build_tiles = (int)(te - tb), build_grid = std::max(1, std::min(build_tiles, 2 * h->sm_count));
     S.n_tiles = (int)h->n_tiles;
     S.grid = grid;
-    S.matrix_bytes = stored ? (int64_t)build_tiles * TILE_ELEMS * 8 : 0;
+    S.matrix_bytes = stored ? (int64_t)build_tiles * TILE_ELEMS * 8
+                            : (h->st_store_end > h->st_begin
+                                   ? (h->st_pre_host[(size_t)h->st_store_end] - h->st_pre_host[(size_t)h->st_begin]) *
+                                         (int64_t)TILE_ELEMS * 8
+                                   : 0);
     // three phase markers come from the handle's event pool (no create/destroy per run, nothing
     // to leak on the error paths below)
     cudaEvent_t ev0 = h->next_event(), ev1 = h->next_event(), ev2 = h->next_event();
@@ -1203,6 +1243,9 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     A.srow_end = h->srow_end;
     A.nchunk = dp / RC_DK;
     A.opT = h->opT.as<double>();
+    A.qst = h->qst.as<double>();
+    A.st_pre = h->st_pre.as<long long>();
+    A.st_store_end = stored ? 0 : h->st_store_end;
     if (stored) {
         if (build_tiles > 0) {
             k_build_dist<true><<<build_grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
@@ -1225,6 +1268,15 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     }
     if (h->n_ranks > 1)
         if (int rc = reduce_extrema_across_ranks(h, lohi, st)) return rc;
+    if (!stored && h->st_store_end > h->st_begin) {  // store what fits: q of the leading super-tiles
+        RcArgs Bld = A;
+        Bld.st_end = h->st_store_end;
+        Bld.st_store_end = h->st_begin;
+        Bld.m = 1;
+        launch_store_rc(std::max(1, std::min((int)(h->st_store_end - h->st_begin), h->sm_count)), st,
+                        Bld, h->rc_dot);
+        ++h->launches;
+    }
     if (build_tiles > 0 && stored) {
         k_transform<<<4 * h->sm_count, 256, 0, st>>>(h->q.as<double>(),
                                                      (size_t)build_tiles * TILE_ELEMS, lohi);
@@ -1621,7 +1673,7 @@ void cge_b200_destroy(cge_b200_handle *h) {
     for (DevBuf *b :
          {&h->q, &h->tile_ij, &h->tile_ij_full, &h->emb, &h->emb_full, &h->dist, &h->w, &h->w2,
           &h->T0a, &h->T0b, &h->Ta, &h->Tb, &h->Sa, &h->Sb, &h->sraw_a, &h->sraw_b, &h->partA,
-          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->st_ij, &h->opT, &h->nrm, &h->rc_mean, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
+          &h->partB, &h->comm, &h->B, &h->qdiag, &h->lohi, &h->slots, &h->auc_out, &h->fpres, &h->st_ij, &h->opT, &h->nrm, &h->rc_mean, &h->st_pre, &h->qst, &h->diam_strips, &h->diam_packed, &h->diam_norms, &h->diam_tilemax,
           &h->diam_list, &h->diam_ctr, &h->diam_mean, &h->s_pda, &h->s_pdb, &h->s_nda, &h->s_ndb, &h->s_pa,
           &h->s_pb, &h->s_na, &h->s_nb, &h->s_pw, &h->s_pw0a, &h->s_pwla, &h->s_pw0b, &h->s_pwlb,
           &h->s_nw0a, &h->s_nwla, &h->s_nw0b, &h->s_nwlb, &h->s_pq, &h->s_nq})

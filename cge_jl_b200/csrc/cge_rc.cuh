@@ -25,6 +25,11 @@ struct RcArgs : SweepArgs {
                                   // 16-dimension chunk one contiguous [kk][row] block of 16 KB (what one
                                   // cp.async.bulk brings into shared memory); the embedding centred at its
                                   // mean for the row-norm / dot form, the raw embedding otherwise
+    // "store what fits": the super-tiles [st_begin, st_store_end) of this rank keep their q tiles in
+    // HBM (row-major 128 x 128, in the order the CTA walks them) and are read instead of recomputed
+    double *qst;                  // tile t of super-tile st at qst + (st_pre[st] - st_pre[st_begin] + t) * TILE_ELEMS
+    const long long *st_pre;      // [n_st + 1] tiles before super-tile st in the global sequence
+    long long st_store_end;       // <= st_begin: nothing stored
 };
 
 size_t rc_smem_bytes();
@@ -32,6 +37,8 @@ size_t rc_smem_bytes();
 void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const RcArgs &a, bool dot);
 const void *fp_kernel_rc(int directed, int dot);
 void launch_extrema_rc(int grid, cudaStream_t stream, const RcArgs &a, unsigned long long *lohi);
+// fills the q tiles of the super-tiles [a.st_begin, a.st_end) (called with st_end = the stored prefix)
+void launch_store_rc(int grid, cudaStream_t stream, const RcArgs &a, bool dot);
 void launch_reduce_part_rc(const RcArgs &a, const double *part, double *sraw, cudaStream_t stream);
 void launch_rc_pack(const double *emb, const double *mean, int n, int np, int dp, double *opT,
                     double *nrm, cudaStream_t stream);

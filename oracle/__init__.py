@@ -3,5 +3,6 @@
 Nothing under cge_jl_b200/ may import this package.
 """
 from .oracle import (  # noqa: F401
-    OracleMtTrace, OracleTrace, build, dist, host_threads, idx, js, wgcl, wgcl_directed, wgcl_mt,
+    OracleMtTrace, OracleStreamTrace, OracleTrace, build, dist, host_threads, idx, js, wgcl,
+    wgcl_directed, wgcl_mt, wgcl_stream,
 )

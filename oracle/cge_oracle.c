@@ -30,9 +30,11 @@
  *   - `max_alphas` (<= 40) lets bench.py time a bounded prefix of the alpha grid.
  *   - Julia's sum() is pairwise/SIMD; here sums are sequential (differences ~1e-16 relative).
  */
+#define _POSIX_C_SOURCE 200809L /* clock_gettime under -std=c11 */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 
 #define N_ALPHA 40
@@ -45,7 +47,17 @@ typedef struct {
     double lo, hi;              /* extrema of the raw distance vector (divergence.jl:92) */
     double hi_full;             /* landmark mode: max distance of the full graph (:113) */
     double final_diff;          /* last max|w-S| */
+    /* wGCL only: seconds spent in the O(n^2) phases -- D build (:79-93), GD = (1-D)^alpha (:142-148),
+     * fixed-point passes (:150-168), P (:170-176), B (:228-234) -- so that bench.py can extrapolate a
+     * bounded sample to a configuration whose arrays fit no host, phase by phase */
+    double t_phase[5];
 } cge_oracle_trace;
+
+static double now_s(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
 
 /* auxilary.jl:57-59 (1-based, i <= j) */
 int64_t cge_oracle_idx(int64_t n, int64_t i, int64_t j) {
@@ -195,9 +207,10 @@ int cge_oracle_wgcl(int64_t m, const int64_t *e_src, const int64_t *e_dst, const
     if (n_distances != n) return -3;                                               /* :81 */
     int64_t p_len = n * (n + 1) / 2;
     double lo, hi;
+    double tph = now_s();
     double *D = build_D(n, embed, d, distances, &lo, &hi);                         /* :79-93 */
     if (!D) return -4;
-    if (tr) { tr->lo = lo; tr->hi = hi; }
+    if (tr) { tr->lo = lo; tr->hi = hi; tr->t_phase[0] += now_s() - tph; }
 
     int64_t adj_n = landmarks ? n_full : n;                                        /* :95-102 */
     double *full_D = NULL;
@@ -220,9 +233,12 @@ int cge_oracle_wgcl(int64_t m, const int64_t *e_src, const int64_t *e_dst, const
     for (a = 1; a <= N_ALPHA && a <= max_alphas; ++a) {
         double alpha = AlphaStep * (double)a;
         (void)AlphaMax;
+        tph = now_s();
         for (int64_t k = 0; k < p_len; ++k) GD[k] = pow(1.0 - D[k], alpha);        /* :142-148 */
+        if (tr) tr->t_phase[1] += now_s() - tph;
         double diff = 1.0;                                                         /* :150 */
         int it = 0;
+        tph = now_s();
         while (diff > delta) {                                                     /* :151-168 */
             for (int64_t i = 0; i < n; ++i) S[i] = 0.0;
             for (int64_t i = 1; i <= n; ++i) {
@@ -243,12 +259,14 @@ int cge_oracle_wgcl(int64_t m, const int64_t *e_src, const int64_t *e_dst, const
             diff = f;
             ++it;
         }
-        if (tr) { tr->iters[a - 1] = it; tr->n_alpha_run = a; tr->final_diff = diff; }
+        if (tr) { tr->iters[a - 1] = it; tr->n_alpha_run = a; tr->final_diff = diff; tr->t_phase[2] += now_s() - tph; }
+        tph = now_s();
         for (int64_t i = 1; i <= n; ++i) {                                         /* :170-176 */
             int64_t base = cge_oracle_idx(n, i, i) - 1;
             for (int64_t j = i; j <= n; ++j)
                 P[base + (j - i)] = T[i - 1] * T[j - 1] * GD[base + (j - i)];
         }
+        if (tr) tr->t_phase[3] += now_s() - tph;
         if (!skip_auc && K > 0) {                                                  /* :178-224 */
             int64_t off = (n_sets > 1 ? (int64_t)(a - 1) : 0) * K;
             double sw = 0.0, swin = 0.0;
@@ -284,6 +302,7 @@ int cge_oracle_wgcl(int64_t m, const int64_t *e_src, const int64_t *e_dst, const
             }
         }
         if (!skip_div) {                                                           /* :226-252 */
+            tph = now_s();
             for (int64_t k = 0; k < vect_len; ++k) vect_B[k] = 0.0;
             for (int64_t i = 1; i <= n; ++i) {
                 int64_t base = cge_oracle_idx(n, i, i) - 1;
@@ -293,6 +312,7 @@ int cge_oracle_wgcl(int64_t m, const int64_t *e_src, const int64_t *e_dst, const
                     vect_B[cge_oracle_idx(n_parts, k, l) - 1] += P[base + (j - i)];
                 }
             }
+            if (tr) tr->t_phase[4] += now_s() - tph;
             double f, div_int = 0.0, div_ext = 0.0;
             if (!split) {
                 f = cge_oracle_js(vect_C, vect_B, NULL, 1, vect_len);

@@ -27,11 +27,12 @@ class OracleTrace(C.Structure):
         ("hi", C.c_double),
         ("hi_full", C.c_double),
         ("final_diff", C.c_double),
+        ("t_phase", C.c_double * 5),  # wGCL: seconds in D build, GD, passes, P, B
     ]
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(_HERE, f) for f in ("cge_oracle.c", "cge_oracle_mt.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("cge_oracle.c", "cge_oracle_mt.c", "cge_oracle_stream.c")]
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(map(os.path.getmtime, srcs)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "libcge_oracle.so"])
     return _SO
@@ -226,4 +227,58 @@ def wgcl_mt(edges, eweights, comm, embed, vweights, samples=None, max_alphas=N_A
     lib.cge_oracle_mt_set_dist_form(0)
     if rc != 0:
         raise RuntimeError(f"parallel oracle error {rc}")
+    return out, tr
+
+
+class OracleStreamTrace(C.Structure):
+    _fields_ = [
+        ("n_alpha_run", C.c_int32),
+        ("iters", C.c_int32 * N_ALPHA),
+        ("div", C.c_double * N_ALPHA),
+        ("auc", C.c_double * N_ALPHA),
+        ("lo", C.c_double),
+        ("hi", C.c_double),
+        ("threads", C.c_int32),
+        ("cached", C.c_int32),
+        ("seconds", C.c_double),
+    ]
+
+
+def wgcl_stream(edges, eweights, comm, embed, vweights, samples=None, directed=False,
+                max_alphas=N_ALPHA, n_threads=0, mem_budget=0):
+    """cge_oracle_stream.c: exact-mode ``wGCL`` / ``wGCL_directed`` (divergence.jl:27-257 / 282-561)
+    without any O(n^2) array, on ``n_threads`` cores (0 = all) -- the CPU answer for BASELINE configs
+    3 and 4, where the reference's packed arrays fit no host.  ``mem_budget`` bytes may be used to
+    keep the per-pair q after the first sweep (same values, faster).  Returns (out[7], trace)."""
+    lib = _load()
+    edges = _i64(edges)
+    src, dst = _i64(edges[:, 0]), _i64(edges[:, 1])
+    ew, cm, em, vw = _f64(eweights), _i64(np.asarray(comm).reshape(-1)), _f64(embed), _f64(vweights)
+    n = int(max(src.max(), dst.max()))
+    if cm.shape[0] != n:
+        raise AssertionError("No. communities not matching no. vertices")
+    if samples is None:
+        K, ns = 0, 1
+        pi = pj = ni = nj = np.zeros(1, dtype=np.int64)
+        pw = np.zeros(1)
+    else:
+        pi, pj, pw, ni, nj = samples
+        pi, pj, ni, nj = (np.atleast_2d(_i64(x)) for x in (pi, pj, ni, nj))
+        pw = np.atleast_2d(_f64(pw))
+        ns, K = pi.shape
+    i64, f64 = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+    lib.cge_oracle_stream.argtypes = [C.c_int, C.c_int64, i64, i64, f64, C.c_int64, i64, f64, C.c_int64,
+                                      f64, C.c_int64, C.c_int64, i64, i64, f64, i64, i64, C.c_int,
+                                      C.c_int, C.c_int64, f64, C.POINTER(OracleStreamTrace)]
+    lib.cge_oracle_stream.restype = C.c_int
+    out = np.zeros(7)
+    tr = OracleStreamTrace()
+    rc = lib.cge_oracle_stream(int(bool(directed)), src.shape[0], _p(src, C.c_int64),
+                               _p(dst, C.c_int64), _p(ew, C.c_double), n, _p(cm, C.c_int64),
+                               _p(em, C.c_double), em.shape[1], _p(vw, C.c_double), K, ns,
+                               _p(pi, C.c_int64), _p(pj, C.c_int64), _p(pw, C.c_double),
+                               _p(ni, C.c_int64), _p(nj, C.c_int64), int(max_alphas), int(n_threads),
+                               int(mem_budget), _p(out, C.c_double), C.byref(tr))
+    if rc != 0:
+        raise RuntimeError(f"streaming oracle error {rc}")
     return out, tr

@@ -9,7 +9,10 @@ arrays (SURVEY.md section 7 "Reference infeasibility"):
   python scripts/run_config.py --config 3                       # 1 GPU
   torchrun --nproc-per-node 8 scripts/run_config.py --config 4  # tiles sharded over 8 GPUs
 
-Appends one JSON line per run to profiles/r01_config_runs.jsonl (rank 0).
+  torchrun --nproc-per-node 8 scripts/run_config.py --config 5 --exact --max-alphas 2   # 1M vertices
+
+Appends one JSON line per run to gpurun_out/config_runs.jsonl (rank 0); the committed copies are
+profiles/r01_config_runs.jsonl and profiles/r02_config_runs.jsonl.
 """
 import argparse
 import json
@@ -26,6 +29,7 @@ from cge_jl_b200.landmarks import landmarks, split_cluster_rss  # noqa: E402
 from cge_jl_b200.synth import abcd_like, planted_partition  # noqa: E402
 
 LANDMARKS = 0
+EXACT = False
 EMPTY = (np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int64), np.zeros(0),
          np.zeros((0, 0)))
 
@@ -64,9 +68,14 @@ def build(cfg):
     elif cfg == 4:
         edges, ew, vw, comm, emb = abcd_like(200000, k=64, d=128, seed=1004)
         name = "synthetic 200k-node ABCD-style graph, 64 communities, d=128, exact"
+    elif cfg == 5 and EXACT:
+        # the exact half of BASELINE.json configs[4]: 1M vertices, d = 128, 5e11 pairs = 4 TB of q:
+        # recompute regime (+ what fits of the matrix kept in HBM), super-tiles sharded over the ranks
+        edges, ew, vw, comm, emb = planted_partition(1000000, k=64, d=128, seed=1005)
+        name = "synthetic 1M-node planted-partition graph, d=128, k=64, exact (--force-exact)"
     elif cfg == 5:
         # the landmark half of BASELINE.json configs[4]: 1M vertices, d = 128, rss landmarks -l 4000
-        # on one GPU (the exact half needs 4 TB of pairs: recompute regime at scale, not in round 1)
+        # on one GPU
         edges, ew, vw, comm, emb = planted_partition(1000000, k=64, d=128, seed=1005)
         name = "synthetic 1M-node planted-partition graph, d=128, k=64, rss landmarks -l 4000 (1 GPU)"
         by = {}
@@ -92,7 +101,11 @@ def main():
     ap.add_argument("--regime", type=int, default=0)
     ap.add_argument("--driver", type=int, default=0, help="0 auto, 1 host loop, 2 persistent, 3 TMA ring")
     ap.add_argument("--max-alphas", type=int, default=0)
+    ap.add_argument("--exact", action="store_true", help="config 5: the exact half (--force-exact)")
+    ap.add_argument("--spot", type=int, default=0, help="vertices of the NumPy degree-sum spot check")
     args = ap.parse_args()
+    global EXACT
+    EXACT = args.exact
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -153,12 +166,27 @@ def main():
         outs = [None] * world
         dist.all_gather_object(outs, out.tolist())
         checks["ranks_agree"] = bool(all(o == outs[0] for o in outs))
+    if args.spot > 0 and rank == 0 and not c["directed"] and c["lm"] is None:
+        # sub-block spot check: S of a few vertices from scratch in NumPy (scripts/spotcheck.py)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from spotcheck import degree_sum_spot_check
+        t0 = time.perf_counter()
+        rows = np.random.default_rng(5).integers(0, n, size=args.spot)
+        worst = degree_sum_spot_check(c["emb"], sc.debug_read(1, n), sc.debug_read(3, n), c["vw"],
+                                      float(st.hi), 0.25 * int(st.n_alpha_run), rows)
+        checks["spot_check_rows"] = int(args.spot)
+        checks["spot_check_max_rel_diff"] = float(worst)
+        checks["spot_check_ok"] = bool(worst <= 1e-9)
+        checks["spot_check_s"] = time.perf_counter() - t0
     pairs = n_scored * (n_scored + 1) // 2 if not c["directed"] else n_scored * n_scored
     line = {
         "config": args.config, "workload": c["name"], "n_gpus": world, "n_scored": int(n_scored),
         "result": [float(x) for x in out], "alphas": int(st.n_alpha_run),
         "fp_passes": int(st.fp_sweeps), "b_passes": int(st.b_sweeps),
         "driver": int(st.driver), "regime": int(st.regime),
+        "iters": [int(x) for x in list(st.iters)[: int(st.n_alpha_run)]],
+        "div": [float(x) for x in list(st.div)[: int(st.n_alpha_run)]],
+        "auc": [float(x) for x in list(st.auc)[: int(st.n_alpha_run)]],
         "matrix_gb_per_gpu": st.matrix_bytes / 1e9,
         "s_run": t_run, "s_upload": t_upload, "s_sampling": t_sample, "s_generate": c["t_gen"],
         "ms_fp_kernels": float(st.ms_sweeps), "ms_b_kernels": float(st.ms_bsweeps),
@@ -168,6 +196,18 @@ def main():
                            / (float(st.ms_sweeps) * 1e-3) / 1e9 if st.ms_sweeps > 0 else None,
         "checks": checks,
     }
+    if int(st.regime) >= 2 and st.ms_sweeps > 0:
+        # recompute regime: FP64 roofline, (2d + 6) flop per recomputed pair and pass;
+        # pairs whose q tile is kept in HBM ("store what fits") are not counted as flops
+        d_emb = c["emb"].shape[1] if c["lm"] is None else c["lm"][1].shape[1]
+        upairs = n_scored * (n_scored + 1) // 2
+        rc_pairs = max(upairs / world - st.matrix_bytes / 8.0, 0.0)
+        tf = (2.0 * d_emb + 6.0) * rc_pairs * int(st.fp_sweeps) / (float(st.ms_sweeps) * 1e-3) / 1e12
+        peak = sc.fp64_peak_tflops()
+        line.update({"recomputed_pair_share": rc_pairs / (upairs / world), "tflops_per_gpu_fp": tf,
+                     "fp64_peak_tflops": peak, "fp64_frac": tf / peak,
+                     "fp64_frac_note": "upper bound when part of the matrix is read from HBM: the pass "
+                                       "time also covers the stored tiles"})
     if rank == 0:
         print(json.dumps(line))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -191,6 +191,25 @@ def test_recompute_row_norm_dot_form(scorer, directed, n, k, d):
     assert_parity(out, stats, ref, tr)
 
 
+@pytest.mark.parametrize("sb,store_mb", [(1, 1), (2, 2), (2, 100)])
+@pytest.mark.parametrize("directed", [False, True])
+def test_recompute_store_what_fits(scorer, directed, sb, store_mb, monkeypatch):
+    """"Store what fits": the leading super-tiles of the rank keep their q tiles in HBM (here a
+    budget of 1-2 MB = 8-16 of the 45 tiles, or everything) and are read in every pass, the rest is
+    recomputed; the mix must meet the same parity bars."""
+    monkeypatch.setenv("CGE_B200_RC_SB", str(sb))
+    monkeypatch.setenv("CGE_B200_STORE_MB", str(store_mb))
+    n = 1100
+    edges, ew, vw, comm, emb = planted_partition(n, 6, 40, seed=31 + directed, directed=directed,
+                                                 weighted=True)
+    out, stats, ref, tr = run_pair(scorer, directed, edges, ew, comm, emb, np.zeros(n), vw,
+                                   driver=2, regime=2)
+    assert stats.regime == 2
+    tiles = stats.matrix_bytes // 131072
+    assert stats.matrix_bytes % 131072 == 0 and (tiles == 45 if store_mb == 100 else 0 < tiles <= 8 * store_mb)
+    assert_parity(out, stats, ref, tr)
+
+
 def test_recompute_branch_free_math_matches_ieee(scorer):
     """The recompute epilogue's branch-free sqrt / divide return the bits of the IEEE operations
     (2^26 pseudo-random operands in the epilogue's ranges, zeros included; operands under 2^-943
