@@ -885,7 +885,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
             for (int64_t c = 0; c < p->d; ++c) mean[(size_t)c] /= (double)n;
         }
         if ((rc = upload_vec(h->rc_mean, mean.data(), mean.size() * 8, st))) return rc;
-        if ((rc = h->opT.ensure((size_t)np * (size_t)dp * 8))) return rc;
+        if ((rc = h->opT.ensure((size_t)h->nb * (size_t)(dp / RC_DK) * RC_CHUNK * 8))) return rc;
         if ((rc = h->nrm.ensure((size_t)np * 8))) return rc;
         launch_rc_pack(h->emb.as<double>(), h->rc_mean.as<double>(), (int)n, (int)np, (int)dp,
                        h->opT.as<double>(), h->rc_dot ? h->nrm.as<double>() : nullptr, st);

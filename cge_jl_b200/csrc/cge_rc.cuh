@@ -6,7 +6,9 @@
 namespace cge {
 
 constexpr int RC_DK = 16;                    // embedding dimensions per staged chunk
-constexpr int RC_CHUNK = RC_DK * TILE;       // doubles of one operand chunk: [kk][row], 16 KB
+constexpr int RC_LD = TILE + 4;              // doubles per kk row of a chunk: 128 rows + 4 pad (bank-conflict-free
+                                             // fragment loads: 132 * 8 B shifts consecutive kk by 8 banks)
+constexpr int RC_CHUNK = RC_DK * RC_LD;      // doubles of one operand chunk: [kk][132], 16.5 KB
 constexpr int RC_MAX_SB = 8;                 // largest super-block (tile rows / columns per super-tile)
 
 // Work of the recompute regime is dealt in SUPER-TILES: sb x sb tiles (sb = 1, 2, 4 or 8; only the
@@ -22,7 +24,7 @@ struct RcArgs : SweepArgs {
     int srow_begin, srow_end;     // super-rows I touched by [st_begin, st_end) (end < begin: none)
     int nchunk;                   // dp / RC_DK
     const double *opT;            // operand image of the Gram / difference loop: per 128-row block and
-                                  // 16-dimension chunk one contiguous [kk][row] block of 16 KB (what one
+                                  // 16-dimension chunk one contiguous [kk][132] block of 16.5 KB (what one
                                   // cp.async.bulk brings into shared memory); the embedding centred at its
                                   // mean for the row-norm / dot form, the raw embedding otherwise
     // "store what fits": the super-tiles [st_begin, st_store_end) of this rank keep their q tiles in
