@@ -832,7 +832,7 @@ static int do_upload(cge_b200_handle *h, const cge_b200_problem *p) {
                          : !h->rc_dot ? CGE_B200_REGIME_RECOMPUTE_DIFF
                          : want == CGE_B200_REGIME_RECOMPUTE_DOT ? CGE_B200_REGIME_RECOMPUTE_DOT
                                                                  : CGE_B200_REGIME_RECOMPUTE;
-    if (stored || !h->rc_dot) {  // the tile table: stored sweeps, k_build_dist
+    if (stored) {  // the tile table of the stored sweeps and of k_build_dist
         std::vector<int2> tij = make_tile_table(h->nb);
         if ((rc = upload_vec(h->tile_ij, tij.data(), tij.size() * sizeof(int2), st))) return rc;
         CUDA_TRY(cudaStreamSynchronize(st));  // tij is a local
@@ -1254,16 +1254,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                                                                 h->q.as<double>(), lohi);
             ++h->launches;
         }
-    } else if (h->rc_dot) {  // recompute regime: only the extrema are needed up front, in the
-        if (local_tiles > 0) {  // arithmetic the passes will use
-            launch_extrema_rc(grid, st, A, lohi);
-            ++h->launches;
-        }
-    } else if (build_tiles > 0) {  // difference form: the FMA chain of k_build_dist is the passes'
-        k_build_dist<false><<<build_grid, NTHREADS, 0, st>>>(h->emb.as<double>(), dp,
-                                                             h->dist.as<double>(), n,
-                                                             h->tile_ij.as<int2>(), tb, te, nullptr,
-                                                             lohi);
+    } else if (local_tiles > 0) {  // recompute regime: only the extrema are needed up front, in
+        launch_extrema_rc(grid, st, A, lohi, h->rc_dot);  // the arithmetic the passes will use
         ++h->launches;
     }
     if (h->n_ranks > 1)
@@ -1293,13 +1285,12 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         const double *dg = h->landmark ? nullptr : h->dist.as<double>();
         const unsigned long long *lh = h->landmark ? lohi + 2 : lohi;
         const int blocks = (int)((SK + 255) / 256);
-        if (h->rc_dot && !h->landmark) {  // the sampled pairs get the bits the passes use
-            launch_sample_q_dot(h->opT.as<double>(), dp / RC_DK, h->nrm.as<double>(), e, dp,
-                                h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh, SK,
-                                h->s_pq.as<double>(), st);
-            launch_sample_q_dot(h->opT.as<double>(), dp / RC_DK, h->nrm.as<double>(), e, dp,
-                                h->s_nda.as<int>(), h->s_ndb.as<int>(), dg, lh, SK,
-                                h->s_nq.as<double>(), st);
+        if (!stored && !h->landmark) {  // the sampled pairs get the bits the passes use
+            const double *nr = h->rc_dot ? h->nrm.as<double>() : nullptr;
+            launch_sample_q_dot(h->opT.as<double>(), dp / RC_DK, nr, e, dp, h->s_pda.as<int>(),
+                                h->s_pdb.as<int>(), dg, lh, SK, h->s_pq.as<double>(), st);
+            launch_sample_q_dot(h->opT.as<double>(), dp / RC_DK, nr, e, dp, h->s_nda.as<int>(),
+                                h->s_ndb.as<int>(), dg, lh, SK, h->s_nq.as<double>(), st);
         } else {
             k_sample_q<<<blocks, 256, 0, st>>>(e, dp, h->s_pda.as<int>(), h->s_pdb.as<int>(), dg, lh,
                                                h->landmark, SK, h->s_pq.as<double>());

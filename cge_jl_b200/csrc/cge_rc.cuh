@@ -38,12 +38,13 @@ size_t rc_smem_bytes();
 // kind: 0 = fixed-point pass undirected, 1 = directed, 2 = B undirected, 3 = B directed
 void launch_tiles_rc(int kind, int grid, cudaStream_t stream, const RcArgs &a, bool dot);
 const void *fp_kernel_rc(int directed, int dot);
-void launch_extrema_rc(int grid, cudaStream_t stream, const RcArgs &a, unsigned long long *lohi);
+void launch_extrema_rc(int grid, cudaStream_t stream, const RcArgs &a, unsigned long long *lohi, bool dot);
 // fills the q tiles of the super-tiles [a.st_begin, a.st_end) (called with st_end = the stored prefix)
 void launch_store_rc(int grid, cudaStream_t stream, const RcArgs &a, bool dot);
 void launch_reduce_part_rc(const RcArgs &a, const double *part, double *sraw, cudaStream_t stream);
 void launch_rc_pack(const double *emb, const double *mean, int n, int np, int dp, double *opT,
                     double *nrm, cudaStream_t stream);
+// q of sampled pairs in the regime's arithmetic; nrm == nullptr selects the difference form
 void launch_sample_q_dot(const double *opT, int nchunk, const double *nrm, const double *emb, int dp,
                          const int *ia, const int *ib, const double *diag,
                          const unsigned long long *lohi, long long count, double *out,

@@ -213,8 +213,9 @@ class Scorer:
         return (oi, oj, draws.value) if return_draws else (oi, oj)
 
     def selftest_math(self, n_samples, seed=1):
-        """(sqrt mismatches, divide mismatches) of the recompute epilogue's branch-free forms
-        against the IEEE operations on ``n_samples`` pseudo-random operands."""
+        """(square roots, normalisations) of the recompute epilogue's short branch-free forms that
+        land more than 2 ulp from the correctly rounded operations on ``n_samples`` pseudo-random
+        operands (``cge_b200_selftest_math``)."""
         a, b = C.c_int64(), C.c_int64()
         _check(self._lib.cge_b200_selftest_math(self._h, int(n_samples), int(seed), C.byref(a),
                                                 C.byref(b)))

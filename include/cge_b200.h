@@ -223,11 +223,13 @@ int cge_b200_table_dims(const char *path, int64_t skip_rows, int32_t n_threads, 
 int cge_b200_read_table(const char *path, int64_t skip_rows, int32_t n_threads, int64_t rows,
                         int64_t cols, int64_t row_stride, int64_t col_stride, double *out);
 
-/* Self-test of the recompute regime's arithmetic: its epilogue evaluates sqrt and divide with
- * branch-free instruction sequences (so that 8 pairs interleave in the FP64 pipe) that must return
- * the bits of the IEEE operations the stored regime and the reference use (Julia sqrt and /,
- * divergence.jl:92, auxilary.jl:19).  Runs n_samples pseudo-random operands in the epilogue's
- * ranges through both and counts the results that differ. */
+/* Self-test of the recompute regime's arithmetic: its epilogue evaluates the square roots and the
+ * normalisation 1 - (D - lo)/(hi - lo) with short branch-free instruction sequences (so that 8 pairs
+ * interleave in the FP64 pipe) instead of the correctly rounded sqrt and divide the stored regime
+ * and the reference use (Julia sqrt and /, divergence.jl:92, auxilary.jl:19).  Runs n_samples
+ * pseudo-random operands in the epilogue's ranges through both and counts the results farther
+ * than 2 ulp from the correctly rounded ones (square roots; normalisations, which must also be
+ * exactly 0 at D = hi). */
 int cge_b200_selftest_math(cge_b200_handle *h, int64_t n_samples, uint64_t seed,
                            int64_t *sqrt_mismatches, int64_t *div_mismatches);
 

@@ -210,10 +210,11 @@ def test_recompute_store_what_fits(scorer, directed, sb, store_mb, monkeypatch):
     assert_parity(out, stats, ref, tr)
 
 
-def test_recompute_branch_free_math_matches_ieee(scorer):
-    """The recompute epilogue's branch-free sqrt / divide return the bits of the IEEE operations
-    (2^26 pseudo-random operands in the epilogue's ranges, zeros included; operands under 2^-943
-    must come back as exactly 0, the documented select)."""
+def test_recompute_branch_free_math_stays_within_2_ulp(scorer):
+    """The recompute epilogue's short branch-free forms -- sqrt from the MUFU.RSQ64H seed and one cubic
+    step, (hi - D) * 1/(hi - lo) for the normalisation -- against the correctly rounded sqrt and
+    divide the stored regime and the reference use: 2^26 pseudo-random operands in the epilogue's
+    ranges, none farther than 2 ulp, zeros and operands under 2^-943 exactly 0, D = hi exactly 0."""
     assert scorer.selftest_math(1 << 26, seed=2024) == (0, 0)
 
 
