@@ -12,7 +12,7 @@ import numpy as np
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 from . import landmarks, parseargs
-from .divergence import wGCL, wGCL_directed
+from .divergence import Scorer, wGCL, wGCL_directed
 
 
 def main(argv=None):
@@ -23,14 +23,20 @@ def main(argv=None):
     init_vweights, init_eweights = np.zeros(0), np.zeros(0)
     init_embed = np.zeros((0, 0))
     v_to_l = np.zeros(0, dtype=np.int64)
-    if land != -1:
-        init_edges, init_vweights = edges.copy(), vweights.copy()
-        init_eweights, init_embed = weights.copy(), embed.copy()
-        distances, embed, comm, edges, weights, vweights, v_to_l = landmarks(
-            edges, weights, vweights, clusters, comm, embed, verbose, land, forced, method, directed)
-    f = wGCL_directed if directed else wGCL
-    results = f(edges, weights, comm, embed, distances, vweights, init_vweights, v_to_l,
-                init_edges, init_eweights, init_embed, split, seed, samples, verbose)
+    sc = Scorer()  # one device handle for the landmark aggregation and the scoring call
+    try:
+        if land != -1:
+            init_edges, init_vweights = edges.copy(), vweights.copy()
+            init_eweights, init_embed = weights.copy(), embed.copy()
+            # selection on the host (north_star), aggregation on the device
+            distances, embed, comm, edges, weights, vweights, v_to_l = landmarks(
+                edges, weights, vweights, clusters, comm, embed, verbose, land, forced, method,
+                directed, device=sc)
+        f = wGCL_directed if directed else wGCL
+        results = f(edges, weights, comm, embed, distances, vweights, init_vweights, v_to_l,
+                    init_edges, init_eweights, init_embed, split, seed, samples, verbose, scorer=sc)
+    finally:
+        sc.close()
     print([float(x) for x in results])
     return results
 

@@ -69,7 +69,7 @@ EXPORTS = [
     "cge_b200_shard_plan", "cge_b200_debug_read", "cge_b200_p2p_handle_size",
     "cge_b200_p2p_export", "cge_b200_p2p_import", "cge_b200_measure_fp64_peak",
     "cge_b200_selftest_math", "cge_b200_sample_non_edges", "cge_b200_table_dims",
-    "cge_b200_read_table", "cge_b200_measure_fp64_pipes",
+    "cge_b200_read_table", "cge_b200_measure_fp64_pipes", "cge_b200_landmarks_aggregate",
 ]
 
 _lib = None
@@ -113,6 +113,9 @@ def load():
     lib.cge_b200_read_table.argtypes = [C.c_char_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
                                         C.c_int64, C.c_int64, _pd]
     lib.cge_b200_selftest_math.argtypes = [vp, C.c_int64, C.c_uint64, _pi, _pi]
+    lib.cge_b200_landmarks_aggregate.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, _pi, C.c_int32, _pd, _pi,
+                                                 _pd, C.c_int64, C.c_int64, C.c_int64, _pi, _pi, _pd,
+                                                 C.c_int32, _pd, _pd, _pd, _pi, _pi, _pi, _pd, C.c_int64, _pi]
     lib.cge_b200_debug_read.argtypes = [vp, C.c_int, _pd, C.c_int64]
     _lib = lib
     return lib

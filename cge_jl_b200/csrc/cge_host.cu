@@ -8,6 +8,7 @@
 // section 8(a).
 #include "../../include/cge_b200.h"
 #include "cge_kernels.cuh"
+#include "cge_landmarks.cuh"
 #include "cge_rc.cuh"
 #include "cge_ring.cuh"
 
@@ -1948,6 +1949,102 @@ int cge_b200_sample_non_edges(cge_b200_handle *h, int64_t n, int64_t m, const in
     release();
     if (rc) return rc;
     CUDA_TRY(e);
+    return 0;
+}
+
+int cge_b200_landmarks_aggregate(cge_b200_handle *h, int64_t n, int64_t d, int64_t n_landmarks,
+                                 const int64_t *landmark, int32_t index_base, const double *vweights,
+                                 const int64_t *comm, const double *embed, int64_t embed_row_stride,
+                                 int64_t embed_col_stride, int64_t m, const int64_t *edge_src,
+                                 const int64_t *edge_dst, const double *eweights, int32_t directed,
+                                 double *out_embed, double *out_lweight, double *out_dii,
+                                 int64_t *out_cluster, int64_t *out_edge_src, int64_t *out_edge_dst,
+                                 double *out_eweights, int64_t edge_cap, int64_t *out_n_edges) {
+    if (!h || n <= 0 || d <= 0 || n_landmarks <= 0 || n >= ((int64_t)1 << 31) ||
+        n_landmarks >= ((int64_t)1 << 31) || m < 0 || m >= ((int64_t)1 << 31) || !landmark ||
+        !vweights || !embed || !out_embed || !out_lweight || !out_dii ||
+        (index_base != 0 && index_base != 1) || (out_cluster && !comm) ||
+        (m > 0 && (!edge_src || !edge_dst || !eweights || !out_edge_src || !out_edge_dst ||
+                   !out_eweights || !out_n_edges)))
+        return fail(CGE_B200_ERR_ARG, "bad landmarks_aggregate argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    const int64_t N = n_landmarks;
+    // row-major copy of the embedding (the caller's matrix may be column-major)
+    std::vector<double> x((size_t)(n * d));
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t j = 0; j < d; ++j)
+            x[(size_t)(i * d + j)] = embed[i * embed_row_stride + j * embed_col_stride];
+    std::vector<int64_t> zero_comm;
+    if (!comm) {
+        zero_comm.assign((size_t)n, 0);
+        comm = zero_comm.data();
+    }
+    DevBuf d_lm, d_vw, d_comm, d_x, d_src, d_dst, d_ew, d_embed, d_lw, d_dii, d_cl, d_oa, d_ob, d_ow;
+    auto release = [&]() {
+        for (DevBuf *b : {&d_lm, &d_vw, &d_comm, &d_x, &d_src, &d_dst, &d_ew, &d_embed, &d_lw, &d_dii,
+                          &d_cl, &d_oa, &d_ob, &d_ow})
+            b->release();
+    };
+    const size_t mm = (size_t)std::max<int64_t>(m, 1);
+    int rc = 0;
+    if (!rc) rc = upload_vec(d_lm, landmark, (size_t)n * 8, st);
+    if (!rc) rc = upload_vec(d_vw, vweights, (size_t)n * 8, st);
+    if (!rc) rc = upload_vec(d_comm, comm, (size_t)n * 8, st);
+    if (!rc) rc = upload_vec(d_x, x.data(), x.size() * 8, st);
+    if (!rc) rc = upload_vec(d_src, edge_src, (size_t)m * 8, st);
+    if (!rc) rc = upload_vec(d_dst, edge_dst, (size_t)m * 8, st);
+    if (!rc) rc = upload_vec(d_ew, eweights, (size_t)m * 8, st);
+    if (!rc) rc = d_embed.ensure((size_t)(N * d) * 8);
+    if (!rc) rc = d_lw.ensure((size_t)N * 8);
+    if (!rc) rc = d_dii.ensure((size_t)N * 8);
+    if (!rc) rc = d_cl.ensure((size_t)N * 8);
+    if (!rc) rc = d_oa.ensure(mm * 8);
+    if (!rc) rc = d_ob.ensure(mm * 8);
+    if (!rc) rc = d_ow.ensure(mm * 8);
+    int cells = 0, bad = 0;
+    cudaError_t e = cudaSuccess;
+    if (!rc)
+        e = landmarks_aggregate_device((int)n, (int)d, (int)N, index_base, d_lm.as<long long>(),
+                                       d_vw.as<double>(), d_comm.as<long long>(), d_x.as<double>(), m,
+                                       d_src.as<long long>(), d_dst.as<long long>(), d_ew.as<double>(),
+                                       directed, d_embed.as<double>(), d_lw.as<double>(),
+                                       d_dii.as<double>(), d_cl.as<long long>(), d_oa.as<long long>(),
+                                       d_ob.as<long long>(), d_ow.as<double>(), &cells, &bad, st);
+    std::vector<long long> oa((size_t)cells), ob((size_t)cells), cl((size_t)N);
+    std::vector<double> ow((size_t)cells);
+    auto step = [&](cudaError_t r) {
+        if (e == cudaSuccess) e = r;
+    };
+    if (!rc && e == cudaSuccess && bad == 0) {
+        step(cudaMemcpyAsync(out_embed, d_embed.p, (size_t)(N * d) * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(out_lweight, d_lw.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(out_dii, d_dii.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+        step(cudaMemcpyAsync(cl.data(), d_cl.p, (size_t)N * 8, cudaMemcpyDeviceToHost, st));
+        if (cells > 0) {
+            step(cudaMemcpyAsync(oa.data(), d_oa.p, (size_t)cells * 8, cudaMemcpyDeviceToHost, st));
+            step(cudaMemcpyAsync(ob.data(), d_ob.p, (size_t)cells * 8, cudaMemcpyDeviceToHost, st));
+            step(cudaMemcpyAsync(ow.data(), d_ow.p, (size_t)cells * 8, cudaMemcpyDeviceToHost, st));
+        }
+        step(cudaStreamSynchronize(st));
+    }
+    release();
+    if (rc) return rc;
+    CUDA_TRY(e);
+    if (bad > 0)
+        return fail(CGE_B200_ERR_ARG, std::to_string(bad) + " landmark ids or edge endpoints out of range");
+    if (out_cluster)
+        for (int64_t L = 0; L < N; ++L) out_cluster[L] = cl[(size_t)L];
+    int64_t w = 0;
+    for (int c = 0; c < cells; ++c) {  // landmark_edges[landmark_edges[:,3] .> 0, :] (landmarks.jl:461)
+        if (!(ow[(size_t)c] > 0.0)) continue;
+        if (w >= edge_cap) return fail(CGE_B200_ERR_ARG, "edge_cap too small");
+        out_edge_src[w] = oa[(size_t)c] + index_base;
+        out_edge_dst[w] = ob[(size_t)c] + index_base;
+        out_eweights[w] = ow[(size_t)c];
+        ++w;
+    }
+    if (out_n_edges) *out_n_edges = w;
     return 0;
 }
 

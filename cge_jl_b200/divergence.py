@@ -212,6 +212,33 @@ class Scorer:
             C.byref(draws)))
         return (oi, oj, draws.value) if return_draws else (oi, oj)
 
+    def landmarks_aggregate(self, landmark, vweights, comm, embedding, edges, eweights, directed,
+                            n_landmarks=None):
+        """``cge_b200_landmarks_aggregate``: the aggregation half of
+        ``landmarks()`` (landmarks.jl:387-463) on the device, from the 1-based vertex -> landmark
+        assignment of ``runsplit``.  Returns ``(dii, embed, cluster, landmark_edges, weights,
+        lweight)`` in the reference's conventions (1-based ids, ``cluster`` as a column)."""
+        lm = _i64(landmark)
+        vw, em, ew = _f64(vweights), np.asarray(embedding, dtype=np.float64), _f64(eweights)
+        cm = _i64(np.asarray(comm).reshape(-1))
+        edges = _i64(edges).reshape(-1, 2)
+        src, dst = _i64(edges[:, 0]), _i64(edges[:, 1])
+        n, d = em.shape
+        N = int(n_landmarks if n_landmarks is not None else lm.max())
+        m = edges.shape[0]
+        cap = int(min(m, N * N)) + 1
+        embed, lweight, dii = np.zeros((N, d)), np.zeros(N), np.zeros(N)
+        cluster = np.zeros(N, dtype=np.int64)
+        oa, ob, ow = np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int64), np.zeros(cap)
+        n_e = C.c_int64()
+        _check(self._lib.cge_b200_landmarks_aggregate(
+            self._h, n, d, N, _pi(lm), 1, _pd(vw), _pi(cm), _pd(em), em.strides[0] // 8,
+            em.strides[1] // 8, m, _pi(src), _pi(dst), _pd(ew), int(bool(directed)), _pd(embed),
+            _pd(lweight), _pd(dii), _pi(cluster), _pi(oa), _pi(ob), _pd(ow), cap, C.byref(n_e)))
+        k = n_e.value
+        return (dii, embed, cluster.reshape(-1, 1), np.stack([oa[:k], ob[:k]], axis=1), ow[:k].copy(),
+                lweight)
+
     def selftest_math(self, n_samples, seed=1):
         """(square roots, normalisations) of the recompute epilogue's short branch-free forms that
         land more than 2 ulp from the correctly rounded operations on ``n_samples`` pseudo-random

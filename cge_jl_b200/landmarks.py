@@ -240,10 +240,13 @@ def _idx(n, i, j):
 
 
 def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land, forced,
-              method, directed):
+              method, directed, device=None):
     """Mirror of ``landmarks(...)`` (landmarks.jl:365-465).
 
     Returns ``(dii, embed, cluster, landmark_edges, weights, lweight, v_to_l)``; all ids 1-based.
+    ``device``: a :class:`cge_jl_b200.divergence.Scorer`; the aggregation after ``runsplit``
+    (landmarks.jl:387-463) then runs on the GPU (``cge_b200_landmarks_aggregate``)
+    and returns the bits of the reference's sequential loops.
     """
     if verbose:
         print("Starts landmark generation")
@@ -259,15 +262,29 @@ def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land
     N = int(lm.max())
     if verbose:
         print(f"Using {N} landmarks")
+    if device is not None:
+        dii, embed, cluster, landmark_edges, lw, lweight = device.landmarks_aggregate(
+            lm, vweights, comm, embedding, edges, weights, directed, N)
+        return dii, embed, cluster, landmark_edges, lw, lweight, lm
+    return aggregate_host(lm, edges, weights, vweights, comm, embedding, directed) + (lm,)
+
+
+def aggregate_host(lm, edges, weights, vweights, comm, embedding, directed):
+    """landmarks.jl:387-463 on the host, in the reference's order of additions (``np.add.at`` and
+    ``np.cumsum`` add sequentially; products and sums are rounded separately as in the Julia loops).
+    The CPU side of tests/test_gpu_landmarks.py; returns everything but ``v_to_l``."""
+    N = int(lm.max())
+    dim = embedding.shape[1]
     l0 = lm - 1
     lweight = np.zeros(N)
     np.add.at(lweight, l0, vweights)
     embed = np.zeros((N, dim))
     np.add.at(embed, l0, vweights[:, None] * embedding)
     embed /= lweight[:, None]
-    # d_ii: unweighted squared deviations over the landmark's weight, then sqrt (landmarks.jl:407-423)
+    # d_ii: unweighted squared deviations over the landmark's weight, then sqrt (landmarks.jl:407-423);
+    # the inner sum over the dimensions runs left to right like the reference's `dist +=`
     dii = np.zeros(N)
-    np.add.at(dii, l0, ((embed[l0] - embedding) ** 2).sum(1))
+    np.add.at(dii, l0, np.cumsum((embed[l0] - embedding) ** 2, axis=1)[:, -1])
     pos = lweight > 0
     dii[pos] = np.sqrt(dii[pos] / lweight[pos])
     cluster = np.zeros(N, dtype=np.int64)
@@ -284,4 +301,4 @@ def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land
         ii, jj = np.nonzero(np.triu(wedges) > 0)  # row-major upper triangle == idx order
     landmark_edges = np.stack([ii + 1, jj + 1], axis=1).astype(np.int64)
     lw = wedges[ii, jj].copy()
-    return dii, embed, cluster, landmark_edges, lw, lweight, lm
+    return dii, embed, cluster, landmark_edges, lw, lweight

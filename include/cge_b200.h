@@ -210,6 +210,28 @@ int cge_b200_sample_non_edges(cge_b200_handle *h, int64_t n, int64_t m, const in
                               int64_t n_samples, int64_t n_sets, uint64_t seed, int64_t *out_i,
                               int64_t *out_j, double *draws_per_sample);
 
+/* SURVEY.md 8(f) F2 -- the aggregation half of landmarks() (landmarks.jl:387-463) on the device.  Landmark
+ * selection (runsplit, landmarks.jl:155-345) stays on the host; given its assignment landmark[i] (index_base-
+ * based, values < n_landmarks + index_base) this call produces every landmark-mode input of wGCL:
+ *   out_embed    n_landmarks x d, row-major: weighted centroids (:387-404)
+ *   out_lweight  n_landmarks: summed vertex weights
+ *   out_dii      n_landmarks: sqrt(sum of UNWEIGHTED squared deviations / lweight) (:407-423)
+ *   out_cluster  n_landmarks: community of the landmark's last member, as passed in comm (:426-430)
+ *   out_edge_*   the weighted landmark edge list in idx order (row-major; upper triangle with self loops
+ *                when undirected), cells with weight > 0 only (:433-463); capacity edge_cap entries
+ *                (min(m, n_landmarks^2) always suffices), *out_n_edges = entries written.
+ * Every sum runs in the reference's order (members in ascending vertex order, edges in file order, products
+ * and sums rounded separately), so the outputs are bit-identical to the Julia loops.  comm may be NULL when
+ * out_cluster is NULL.  embed is addressed as embed[i*row_stride + j*col_stride]. */
+int cge_b200_landmarks_aggregate(cge_b200_handle *h, int64_t n, int64_t d, int64_t n_landmarks,
+                                 const int64_t *landmark, int32_t index_base, const double *vweights,
+                                 const int64_t *comm, const double *embed, int64_t embed_row_stride,
+                                 int64_t embed_col_stride, int64_t m, const int64_t *edge_src,
+                                 const int64_t *edge_dst, const double *eweights, int32_t directed,
+                                 double *out_embed, double *out_lweight, double *out_dii,
+                                 int64_t *out_cluster, int64_t *out_edge_src, int64_t *out_edge_dst,
+                                 double *out_eweights, int64_t edge_cap, int64_t *out_n_edges);
+
 /* SURVEY.md 8(f) F3 -- ingest of the whitespace-delimited numeric tables the reference reads with
  * readdlm(fn, Float64 | Int) (auxilary.jl:86 edgelist, :123 communities, :150-155 embedding), parsed
  * on all host cores straight into the caller's matrix.  Host-only, no GPU needed.
