@@ -16,11 +16,12 @@
 # cge_jl_b200/divergence.py, which IS exercised by the test-suite through the same C ABI.
 module CGEB200
 
+using CGE
 using CGE: parseargs, landmarks, louvain_clust   # re-exported unchanged; wGCL* are defined here
 using StatsBase
 using Random
 
-export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table
+export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table, landmarks_b200
 
 const LIB = get(ENV, "CGE_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "cge_jl_b200", "libcge_b200.so")))
@@ -151,6 +152,51 @@ function draw_samples(adj_edges::Array{Int,2}, adj_eweights::Vector{Float64}, ad
         neg_i[:, s] = [e[1] for e in neg]; neg_j[:, s] = [e[2] for e in neg]
     end
     return pos_i, pos_j, pos_w, neg_i, neg_j
+end
+
+"""
+    landmarks_b200(edges, weights, vweights, clusters, comm, embedding, verbose, land, forced, method, directed)
+
+`CGE.landmarks` (src/landmarks.jl:365-465) with the aggregation after `runsplit` (:387-463) on the device
+(`cge_b200_landmarks_aggregate`, SURVEY.md 8(f) F2): selection stays in Julia, the centroids, weights, d_ii,
+landmark communities and the weighted landmark edge list come back bit-identical to the Julia loops.  Same
+arguments and return tuple as `landmarks`; pass it to `wGCL` unchanged.
+"""
+function landmarks_b200(edges::Array{Int,2}, weights::Vector{Float64}, vweights::Vector{Float64},
+                        clusters::Vector{Vector{Int}}, comm::Array{Int,2}, embedding::Array{Float64,2},
+                        verbose::Bool, land::Int, forced::Int, method::Function, directed::Bool)
+    rows_embed, dim = size(embedding)
+    unique_rows = size(unique(embedding, dims=1), 1)
+    if land > unique_rows
+        @warn "Requested number of clusters larger than unique no. embeddings. Truncating to $unique_rows landmarks."
+        land = unique_rows
+    end
+    lm = CGE.runsplit(embedding, vweights, clusters, land, forced, method) .+ 1      # landmarks.jl:378-379
+    N = Int(maximum(lm)); m = size(edges, 1)
+    embed = zeros(dim, N)                       # filled row-major N x dim by the library = dim x N column-major
+    lweight = zeros(N); dii = zeros(N); cluster = zeros(Int, N)
+    cap = min(m, N * N) + 1
+    oa = zeros(Int, cap); ob = zeros(Int, cap); ow = zeros(cap); n_e = Ref{Int64}(0)
+    src = edges[:, 1]; dst = edges[:, 2]; cm = vec(comm)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cge_b200_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), 0, h))
+    try
+        GC.@preserve lm vweights cm embedding src dst weights begin
+            check(ccall((:cge_b200_landmarks_aggregate, LIB), Cint,
+                        (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Int32, Ptr{Float64}, Ptr{Int64},
+                         Ptr{Float64}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int32,
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64},
+                         Ptr{Float64}, Int64, Ref{Int64}),
+                        h[], rows_embed, dim, N, lm, 1, vweights, cm,
+                        embedding, 1, rows_embed,                 # column-major: row stride 1
+                        m, src, dst, weights, directed ? 1 : 0,
+                        embed, lweight, dii, cluster, oa, ob, ow, cap, n_e))
+        end
+    finally
+        ccall((:cge_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    k = Int(n_e[])
+    return dii, permutedims(embed), reshape(cluster, :, 1), hcat(oa[1:k], ob[1:k]), ow[1:k], lweight, lm
 end
 
 function score(directed::Bool, edges, eweights, comm, embed, distances, vweights, init_vweights,
