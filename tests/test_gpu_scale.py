@@ -173,3 +173,26 @@ def test_abcd_like_unequal_communities(scorer):
     b, sb = _run(scorer, False, small, s2, 2, 2, 2500)
     assert list(sa.iters) == list(sb.iters)
     np.testing.assert_allclose(b, a, rtol=1e-11, atol=1e-15)
+
+
+def test_sub_block_spot_check_of_a_recompute_run(scorer, monkeypatch):
+    """What scripts/run_config.py --config 5 --exact does at 10^6 vertices (SURVEY.md section 7 "(iv)
+    sub-block spot checks at 1M"), at a size the suite can afford: after two alphas of a recompute run
+    with super-tiles and part of the matrix kept in HBM, the degree sums S_i of a few vertices are
+    recomputed from scratch in NumPy over all their partners and must match the device's last pass."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from spotcheck import degree_sum_spot_check
+    monkeypatch.setenv("CGE_B200_RC_SB", "4")
+    monkeypatch.setenv("CGE_B200_STORE_MB", "600")
+    n = 30000
+    data = planted_partition(n, k=12, d=64, seed=31)
+    samples = dv.draw_samples(data[0], data[1], n, 2000, 42, False, True)
+    out, st = dv.wGCL(data[0], data[1], data[3], data[4], np.zeros(n), data[2], *EMPTY, False, 42, 2000,
+                      False, samples=samples, return_stats=True, scorer=scorer, max_alphas=2, regime=2)
+    assert st.regime == 2 and 0 < st.matrix_bytes < 8 * n * n // 2 and st.n_alpha_run == 2
+    rows = np.random.default_rng(3).integers(0, n, size=6)
+    worst = degree_sum_spot_check(data[4], scorer.debug_read(1, n), scorer.debug_read(3, n), data[2],
+                                  float(st.hi), 0.5, rows)
+    assert worst <= 1e-11
