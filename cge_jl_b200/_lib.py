@@ -9,7 +9,8 @@ import os
 
 N_ALPHA = 40
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcge_b200.so")
+# CGE_B200_LIB overrides the location (the variable julia/CGEB200.jl reads as well)
+LIB_PATH = os.environ.get("CGE_B200_LIB") or os.path.join(_HERE, "libcge_b200.so")
 
 OK, ERR_ARG, ERR_ASSERT_COMM, ERR_ASSERT_DIST, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_STATE = (
     0, -1, -2, -3, -4, -5, -6, -7)
