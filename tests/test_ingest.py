@@ -89,3 +89,30 @@ def test_threads_agree_on_a_larger_table(tmp_path):
     assert np.array_equal(ref, a)
     for th in (2, 3, 8, 0):
         assert np.array_equal(readdlm(str(fn), n_threads=th), ref)
+
+
+REF_TEST = "/root/reference/test"
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF_TEST),
+                    reason="the reference checkout exists in the build container only")
+def test_reference_own_fixture_files_through_the_native_reader():
+    """The three command lines of the reference's own test (test/runtests.jl:4-19) on the reference's own
+    files -- 0-based edgelist without a final newline, weighted edgelist, 1- and 2-column .ecg, node2vec /
+    ordered / unordered embeddings -- parsed by the native reader behind `parseargs`: the assertions of
+    runtests.jl:21-41, and the same arrays as the committed fixtures (tests/golden/make_fixtures.py)."""
+    lines = [["-g", "test.edgelist", "-c", "test1col.ecg", "-e", "test_n2v.embedding"],
+             ["-g", "test.edgelist", "-c", "test2col.ecg", "-e", "test_ordered.embedding"],
+             ["-g", "test_weights.edgelist", "-c", "test2col.ecg", "-e", "test_unordered.embedding"]]
+    fixtures = ["test115.npz", "test115.npz", "test115_weighted.npz"]
+    for argv, fx in zip(lines, fixtures):
+        argv = [a if a.startswith("-") else f"{REF_TEST}/{a}" for a in argv] + ["-l", "20", "-f", "1", "-m", "rss"]
+        edges, weights, vweights, comm, clusters, embed, verbose, land, forced, method = parseargs(argv)[:10]
+        assert edges.dtype == np.int64 and edges.ndim == 2 and edges.min() == 1          # runtests.jl:23-24
+        assert weights.dtype == np.float64 and vweights.dtype == np.float64              # :26-27
+        assert comm.dtype == np.int64 and comm.shape[1] == 1 and comm.min() == 1         # :29-31
+        assert isinstance(clusters, list) and embed.dtype == np.float64 and embed.ndim == 2  # :33-34
+        assert verbose is False and land == 20 and forced == 1                           # :36-39
+        e, w, vw, c, emb = load_fixture(fx)
+        assert np.array_equal(edges, e) and np.array_equal(weights, w) and np.array_equal(vweights, vw)
+        assert np.array_equal(comm, c) and np.array_equal(embed, emb)
