@@ -52,6 +52,7 @@ class Stats(C.Structure):
         ("n_ranks", C.c_int32), ("regime", C.c_int32), ("diam_candidate_tiles", C.c_int32),
         ("ms_upload", C.c_float), ("ms_build", C.c_float), ("ms_solve", C.c_float),
         ("ms_total", C.c_float), ("ms_sweeps", C.c_float), ("ms_bsweeps", C.c_float),
+        ("b_fused", C.c_int32), ("reserved", C.c_int32),
     ]
 
     def as_dict(self):
@@ -62,6 +63,9 @@ class Stats(C.Structure):
         return d
 
 
+# cge_b200_eigvec_fn: int (*)(const double *c, int64_t d, double *v, void *user)
+EIGVEC_FN = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_double), C.c_void_p)
+
 EXPORTS = [
     "cge_b200_version", "cge_b200_device_count", "cge_b200_last_error", "cge_b200_score",
     "cge_b200_score_multi",
@@ -71,6 +75,7 @@ EXPORTS = [
     "cge_b200_p2p_export", "cge_b200_p2p_import", "cge_b200_measure_fp64_peak",
     "cge_b200_selftest_math", "cge_b200_sample_non_edges", "cge_b200_table_dims",
     "cge_b200_read_table", "cge_b200_measure_fp64_pipes", "cge_b200_landmarks_aggregate",
+    "cge_b200_landmarks_select", "cge_b200_sym_top_eigvec",
 ]
 
 _lib = None
@@ -117,6 +122,10 @@ def load():
     lib.cge_b200_landmarks_aggregate.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64, _pi, C.c_int32, _pd, _pi,
                                                  _pd, C.c_int64, C.c_int64, C.c_int64, _pi, _pi, _pd,
                                                  C.c_int32, _pd, _pd, _pd, _pi, _pi, _pi, _pd, C.c_int64, _pi]
+    lib.cge_b200_landmarks_select.argtypes = [vp, C.c_int64, C.c_int64, _pd, C.c_int64, C.c_int64, _pd,
+                                              C.c_int64, _pi, _pi, C.c_int32, C.c_int64, C.c_int64,
+                                              C.c_int32, EIGVEC_FN, vp, _pi, _pi]
+    lib.cge_b200_sym_top_eigvec.argtypes = [_pd, C.c_int64, _pd, _pd]
     lib.cge_b200_debug_read.argtypes = [vp, C.c_int, _pd, C.c_int64]
     _lib = lib
     return lib

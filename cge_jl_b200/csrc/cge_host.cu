@@ -1383,11 +1383,83 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     std::vector<double> Bh((size_t)k * k);
     const int ublocks = (n + 255) / 256;
     long long sweep_no = 0;
+    // Deferred B sweep: the global score of alpha m needs one more read of the matrix with the
+    // converged T, and so does the first fixed-point pass of alpha m+1 (T is warm-started), so when
+    // alpha m+1 is certain to run, B of alpha m is computed by k_bfp<m+1> together with that pass
+    // and its score is booked one iteration late -- same numbers, one matrix read less per alpha.
+    bool can_fuse = stored && !small && !h->directed && driver == CGE_B200_DRIVER_PERSISTENT;
+    if (const char *e = getenv("CGE_B200_FUSE_B")) can_fuse = can_fuse && atoi(e) != 0;
+    int pending_b = 0;  // exponent whose B rides on the next alpha's first pass (0: none)
+    char *pin = static_cast<char *>(h->pinned);
+    double *pin_auc = reinterpret_cast<double *>(pin + 64);
+    double *pin_B = reinterpret_cast<double *>(pin + 64 + 2 * AUC_MAX_BLOCKS * 8);
+    // queue the all-reduce (one rank per process) and the read-back of B behind its kernel
+    auto fetch_B = [&]() -> int {
+        if (h->n_ranks > 1 && !h->group)
+            if (int rc = nccl_check(g_nccl.AllReduce(h->B.p, h->B.p, (size_t)k * k, kNcclF64,
+                                                     kNcclSum, h->nccl_comm, st),
+                                    "ncclAllReduce(B)"))
+                return rc;
+        CUDA_TRY(cudaMemcpyAsync(pin_B, h->B.p, (size_t)k * k * 8, cudaMemcpyDeviceToHost, st));
+        return 0;
+    };
+    // after the stream is synchronized: B of exponent mb is in pin_B -> JS score, :226-252 / :530-556
+    auto book_div = [&](int mb) -> int {
+        if (h->n_ranks > 1 && h->group) {  // sum the ranks' B on the host, in rank order
+            LocalGroup &G = *h->group;
+            const size_t kk = (size_t)k * k;
+            std::memcpy(G.B.data() + (size_t)h->rank * kk, pin_B, kk * 8);
+            if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+            for (size_t i = 0; i < kk; ++i) {
+                double acc = 0.0;
+                for (int r = 0; r < G.n; ++r) acc += G.B[(size_t)r * kk + i];
+                pin_B[i] = acc;
+            }
+            if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
+        }
+        std::memcpy(Bh.data(), pin_B, (size_t)k * k * 8);
+        double f, div_int = 0.0, div_ext = 0.0;
+        if (!h->split) {
+            f = js_bins(h->C, Bh, h->bins, h->bin_internal, 0, 1);
+        } else {
+            div_int = js_bins(h->C, Bh, h->bins, h->bin_internal, 1, 1);
+            div_ext = js_bins(h->C, Bh, h->bins, h->bin_internal, 1, 0);
+            f = (div_int + div_ext) / 2.0;
+        }
+        S.div[mb - 1] = f;
+        if (f < best_div) {  // :242-251
+            best_div = f;
+            best_alpha = 0.25 * mb;
+            best_div_ext = !h->split ? 0.0 : div_ext;
+            best_div_int = !h->split ? 0.0 : div_int;
+            alpha_div_counter = 5;
+        } else {
+            alpha_div_counter -= 1;
+            skip_div = alpha_div_counter == 0;
+        }
+        return 0;
+    };
     for (int m = 1; m <= h->max_alphas; ++m) {
         const double alpha = 0.25 * m;
         A.m = m;
         double diff = 1.0, eps = h->directed ? 0.9 : 0.25;  // :150,:34 / :434-435
         int it = 0;
+        const bool fused = pending_b > 0;  // == m - 1
+        A.skip_first_tiles = 0;
+        if (fused) {
+            CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
+            if (local_tiles > 0) {
+                cudaEventRecord(h->next_event(), st);
+                launch_tiles(m, 4, grid, st, A);  // B of m-1 + pass 1 of m
+                cudaEventRecord(h->next_event(), st);
+                h->ev_is_b.push_back(0);  // carries a fixed-point pass: booked with the sweeps
+                ++h->launches;
+            }
+            ++S.b_sweeps;
+            ++S.b_fused;
+            if (int rc = fetch_B()) return rc;
+            A.skip_first_tiles = 1;
+        }
         if (driver == CGE_B200_DRIVER_PERSISTENT || driver == CGE_B200_DRIVER_RING) {
             // one cooperative launch runs every pass of this alpha
             const bool ring = stored && driver == CGE_B200_DRIVER_RING;
@@ -1475,10 +1547,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
         }
         // ---- local score (divergence.jl:178-224 / 478-528) and global score (:226-252 /
         // :530-556): both kernels are queued behind the fixed point, one sync per alpha ----
-        char *pin = static_cast<char *>(h->pinned);
-        double *pin_auc = reinterpret_cast<double *>(pin + 64);
-        double *pin_B = reinterpret_cast<double *>(pin + 64 + 2 * AUC_MAX_BLOCKS * 8);
-        const bool do_auc = !skip_auc, do_div = !skip_div;
+        const bool do_auc = !skip_auc;
         int auc_blocks = 0;
         if (do_auc) {
             const long long off = (h->n_sets > 1 ? (long long)(m - 1) : 0) * h->K;
@@ -1493,7 +1562,19 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
             CUDA_TRY(cudaMemcpyAsync(pin_auc, h->auc_out.p, (size_t)auc_blocks * 16,
                                      cudaMemcpyDeviceToHost, st));
         }
-        if (do_div) {
+        bool synced = false;
+        if (fused) {  // the previous alpha's global score, before this alpha's scores (:226-252)
+            CUDA_TRY(cudaStreamSynchronize(st));
+            synced = true;
+            if (int rc = book_div(m - 1)) return rc;
+            pending_b = 0;
+        }
+        const bool do_div = !skip_div;
+        // alpha m+1 runs for certain when neither score can reach its patience limit at alpha m
+        // (:215-223, :242-253: a counter of c before alpha m is >= c-1 after it)
+        const bool defer = do_div && can_fuse && m < h->max_alphas &&
+                           (alpha_div_counter >= 2 || (do_auc && alpha_auc_counter >= 2));
+        if (do_div && !defer) {
             CUDA_TRY(cudaMemsetAsync(h->B.p, 0, (size_t)k * k * 8, st));
             if (local_tiles > 0) {
                 cudaEventRecord(h->next_event(), st);
@@ -1505,26 +1586,10 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 ++h->launches;
             }
             ++S.b_sweeps;
-            if (h->n_ranks > 1 && !h->group)
-                if (int rc = nccl_check(g_nccl.AllReduce(h->B.p, h->B.p, (size_t)k * k, kNcclF64,
-                                                         kNcclSum, h->nccl_comm, st),
-                                        "ncclAllReduce(B)"))
-                    return rc;
-            CUDA_TRY(cudaMemcpyAsync(pin_B, h->B.p, (size_t)k * k * 8, cudaMemcpyDeviceToHost, st));
+            if (int rc = fetch_B()) return rc;
+            synced = false;
         }
-        CUDA_TRY(cudaStreamSynchronize(st));
-        if (do_div && h->n_ranks > 1 && h->group) {  // sum the ranks' B on the host, in rank order
-            LocalGroup &G = *h->group;
-            const size_t kk = (size_t)k * k;
-            std::memcpy(G.B.data() + (size_t)h->rank * kk, pin_B, kk * 8);
-            if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
-            for (size_t i = 0; i < kk; ++i) {
-                double acc = 0.0;
-                for (int r = 0; r < G.n; ++r) acc += G.B[(size_t)r * kk + i];
-                pin_B[i] = acc;
-            }
-            if (!G.barrier()) return fail(CGE_B200_ERR_STATE, "another rank failed");
-        }
+        if (!synced) CUDA_TRY(cudaStreamSynchronize(st));
         if (driver != CGE_B200_DRIVER_HOSTLOOP) {
             std::memcpy(&it, pin, 4);
             std::memcpy(&diff, pin + 8, 8);
@@ -1553,27 +1618,10 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 skip_auc = alpha_auc_counter == 0;
             }
         }
-        if (do_div) {
-            std::memcpy(Bh.data(), pin_B, (size_t)k * k * 8);
-            double f, div_int = 0.0, div_ext = 0.0;
-            if (!h->split) {
-                f = js_bins(h->C, Bh, h->bins, h->bin_internal, 0, 1);
-            } else {
-                div_int = js_bins(h->C, Bh, h->bins, h->bin_internal, 1, 1);
-                div_ext = js_bins(h->C, Bh, h->bins, h->bin_internal, 1, 0);
-                f = (div_int + div_ext) / 2.0;
-            }
-            S.div[m - 1] = f;
-            if (f < best_div) {  // :242-251
-                best_div = f;
-                best_alpha = alpha;
-                best_div_ext = !h->split ? 0.0 : div_ext;
-                best_div_int = !h->split ? 0.0 : div_int;
-                alpha_div_counter = 5;
-            } else {
-                alpha_div_counter -= 1;
-                skip_div = alpha_div_counter == 0;
-            }
+        if (do_div && !defer) {
+            if (int rc = book_div(m)) return rc;
+        } else if (defer) {
+            pending_b = m;
         }
         if (skip_div && skip_auc) break;  // :253
     }
@@ -1949,6 +1997,60 @@ int cge_b200_sample_non_edges(cge_b200_handle *h, int64_t n, int64_t m, const in
     release();
     if (rc) return rc;
     CUDA_TRY(e);
+    return 0;
+}
+
+int cge_b200_landmarks_select(cge_b200_handle *h, int64_t n, int64_t d, const double *embed,
+                              int64_t embed_row_stride, int64_t embed_col_stride, const double *vweights,
+                              int64_t n_clusters, const int64_t *cluster_ptr, const int64_t *cluster_members,
+                              int32_t index_base, int64_t land, int64_t forced, int32_t rule,
+                              cge_b200_eigvec_fn eig, void *eig_user, int64_t *out_group, int64_t *out_cuts) {
+    if (!h || n <= 0 || d <= 0 || n >= ((int64_t)1 << 31) || d > 4096 || !embed || !vweights ||
+        n_clusters <= 0 || !cluster_ptr || !cluster_members || !out_group || land <= 0 || forced <= 0 ||
+        (index_base != 0 && index_base != 1) ||
+        (rule != CGE_B200_RULE_RSS && rule != CGE_B200_RULE_SIZE && rule != CGE_B200_RULE_DIAMETER))
+        return fail(CGE_B200_ERR_ARG, "bad landmarks_select argument");
+    if (cluster_ptr[0] != 0 || cluster_ptr[n_clusters] != n)
+        return fail(CGE_B200_ERR_ARG, "the clusters must cover every vertex exactly once");
+    std::vector<int> members((size_t)n);
+    std::vector<char> seen((size_t)n, 0);
+    for (int64_t c = 0; c < n_clusters; ++c)
+        if (cluster_ptr[c + 1] < cluster_ptr[c])
+            return fail(CGE_B200_ERR_ARG, "cluster_ptr must be non-decreasing");
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = cluster_members[i] - index_base;
+        if (v < 0 || v >= n || seen[(size_t)v])
+            return fail(CGE_B200_ERR_ARG, "the clusters must cover every vertex exactly once");
+        seen[(size_t)v] = 1;
+        members[(size_t)i] = (int)v;
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    // row-major copy of the embedding (the caller's matrix may be column-major)
+    std::vector<double> x;
+    const double *xr = embed;
+    if (!(embed_col_stride == 1 && embed_row_stride == d)) {
+        x.resize((size_t)(n * d));
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = 0; j < d; ++j)
+                x[(size_t)(i * d + j)] = embed[i * embed_row_stride + j * embed_col_stride];
+        xr = x.data();
+    }
+    std::string msg;
+    long long cuts = 0;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long here");
+    const int rc = landmarks_select_device(h->device, h->stream, n, (int)d, xr, vweights, n_clusters,
+                                           reinterpret_cast<const long long *>(cluster_ptr), members.data(),
+                                           land, forced, rule, reinterpret_cast<SelectEigFn>(eig), eig_user,
+                                           reinterpret_cast<long long *>(out_group), &cuts, msg);
+    if (out_cuts) *out_cuts = cuts;
+    if (rc == -1) return fail(CGE_B200_ERR_CUDA, msg);
+    if (rc == -2) return fail(CGE_B200_ERR_STATE, msg);
+    return 0;
+}
+
+int cge_b200_sym_top_eigvec(const double *a, int64_t d, double *v_out, double *lambda) {
+    if (!a || !v_out || d <= 0 || d > 4096) return fail(CGE_B200_ERR_ARG, "bad sym_top_eigvec argument");
+    sym_top_eigvec(a, (int)d, v_out, lambda);
     return 0;
 }
 

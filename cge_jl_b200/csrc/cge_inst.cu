@@ -15,6 +15,7 @@ namespace cge {
             case 0: k_sweep<MM, false><<<grid, NTHREADS, 0, stream>>>(a); break;  \
             case 1: k_sweep<MM, true><<<grid, NTHREADS, 0, stream>>>(a); break;   \
             case 2: k_bsweep<MM, false><<<grid, NTHREADS, 0, stream>>>(a); break; \
+            case 4: launch_bfp<MM>(grid, stream, a); break;                   \
             default: k_bsweep<MM, true><<<grid, NTHREADS, 0, stream>>>(a); break; \
         }                                                                    \
         break;

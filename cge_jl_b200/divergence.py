@@ -239,6 +239,39 @@ class Scorer:
         return (dii, embed, cluster.reshape(-1, 1), np.stack([oa[:k], ob[:k]], axis=1), ow[:k].copy(),
                 lweight)
 
+    def landmarks_select(self, embedding, vweights, clusters, land, forced, rule, eig="lapack"):
+        """``cge_b200_landmarks_select``: ``runsplit`` (landmarks.jl:279-345) with
+        the cuts of the split rule on the device.  ``clusters``: list of 1-based vertex-id arrays
+        (any order: they are sorted like the reference's ``sort(initial_clusters)``); ``rule``:
+        ``"rss"``, ``"size"`` or ``"diameter"``.  ``eig``: ``"lapack"`` hands the d x d eigenproblem of
+        every cut to ``numpy.linalg.eigh`` through the library's callback (the routine the host mirror
+        calls, sign included); ``"builtin"`` uses the library's own solver (sign fixed: largest-
+        magnitude component positive).  Returns ``(group, cuts)``: 0-based landmark id per vertex, and
+        the number of cluster cuts made."""
+        code = {"rss": 0, "size": 2, "diameter": 3}[rule]
+        em, vw = np.asarray(embedding, dtype=np.float64), _f64(vweights)
+        n, d = em.shape
+        cl = sorted((np.asarray(c, dtype=np.int64) for c in clusters), key=lambda c: c.tolist())
+        ptr = np.zeros(len(cl) + 1, dtype=np.int64)
+        ptr[1:] = np.cumsum([c.size for c in cl])
+        members = _i64(np.concatenate(cl)) if cl else np.zeros(0, dtype=np.int64)
+        group = np.zeros(n, dtype=np.int64)
+        cuts = C.c_int64()
+
+        def _eigh(c, dd, v, _user):
+            try:
+                a = np.ctypeslib.as_array(c, shape=(dd, dd))
+                np.ctypeslib.as_array(v, shape=(dd,))[:] = np.linalg.eigh(a)[1][:, -1]
+                return 0
+            except Exception:  # noqa: BLE001 -- must not unwind through the C frames
+                return 1
+
+        cb = _lib.EIGVEC_FN(_eigh) if eig == "lapack" else C.cast(None, _lib.EIGVEC_FN)
+        _check(self._lib.cge_b200_landmarks_select(
+            self._h, n, d, _pd(em), em.strides[0] // 8, em.strides[1] // 8, _pd(vw), len(cl), _pi(ptr),
+            _pi(members), 1, int(land), int(forced), code, cb, None, _pi(group), C.byref(cuts)))
+        return group, cuts.value
+
     def selftest_math(self, n_samples, seed=1):
         """(square roots, normalisations) of the recompute epilogue's short branch-free forms that
         land more than 2 ulp from the correctly rounded operations on ``n_samples`` pseudo-random

@@ -75,11 +75,21 @@ def _w_mean(m, w):
     return (m * w[:, None]).sum(0) / w.sum()
 
 
+# The sign of an eigenvector is LAPACK's to choose (it decides which child of a cut is "low", i.e. the
+# numbering of the landmarks, not the partition).  CANONICAL_SIGN = True fixes it the way the device
+# selection (cge_b200_landmarks_select) does -- largest-magnitude component positive -- so that the two
+# can be compared label by label; the default keeps whatever LAPACK returns, like the reference.
+CANONICAL_SIGN = False
+
+
 def _pc1(m, w):
     """Projection on the first principal component of the weighted, centred rows."""
     y = (m - _w_mean(m, w)) * np.sqrt(w)[:, None]
     _, vec = np.linalg.eigh(y.T @ y)
-    return y @ vec[:, -1]
+    v = vec[:, -1]
+    if CANONICAL_SIGN and v[int(np.argmax(np.abs(v)))] < 0:
+        v = -v
+    return y @ v
 
 
 def total_rss(m, w):
@@ -244,9 +254,9 @@ def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land
     """Mirror of ``landmarks(...)`` (landmarks.jl:365-465).
 
     Returns ``(dii, embed, cluster, landmark_edges, weights, lweight, v_to_l)``; all ids 1-based.
-    ``device``: a :class:`cge_jl_b200.divergence.Scorer`; the aggregation after ``runsplit``
-    (landmarks.jl:387-463) then runs on the GPU (``cge_b200_landmarks_aggregate``)
-    and returns the bits of the reference's sequential loops.
+    ``device``: a :class:`cge_jl_b200.divergence.Scorer`; ``runsplit`` (``cge_b200_landmarks_select``,
+    SURVEY.md 8(f) F4; rss, size and diameter rules) and the aggregation after it (landmarks.jl:387-463,
+    ``cge_b200_landmarks_aggregate``) then run on the GPU.
     """
     if verbose:
         print("Starts landmark generation")
@@ -256,7 +266,12 @@ def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land
         print(f"Warning: Requested number of clusters larger than unique no. embeddings. "
               f"Truncating to {unique_rows} landmarks.", file=sys.stderr)
         land = unique_rows
-    lm = runsplit(embedding, vweights, clusters, land, forced, method) + 1
+    rule = {split_cluster_rss: "rss", split_cluster_size: "size",
+            split_cluster_diameter: "diameter"}.get(method)
+    if device is not None and rule is not None:  # the cuts run on the GPU
+        lm = device.landmarks_select(embedding, vweights, clusters, land, forced, rule)[0] + 1
+    else:
+        lm = runsplit(embedding, vweights, clusters, land, forced, method) + 1
     if verbose:
         print("Landmarks generated")
     N = int(lm.max())

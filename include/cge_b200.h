@@ -136,7 +136,11 @@ typedef struct cge_b200_stats {
     float ms_solve;                         /* the alpha loop (CUDA events) */
     float ms_total;                         /* wall clock of the call */
     float ms_sweeps;                        /* sum of the fixed-point sweep kernels (CUDA events) */
-    float ms_bsweeps;                       /* sum of the B sweep kernels (CUDA events) */
+    float ms_bsweeps;                       /* sum of the stand-alone B sweep kernels (CUDA events) */
+    int32_t b_fused;                        /* of b_sweeps: B sweeps that rode on the first fixed-point
+                                               pass of the next alpha (one matrix read for both; their
+                                               kernel time is part of ms_sweeps) */
+    int32_t reserved;
 } cge_b200_stats;
 
 typedef struct cge_b200_handle cge_b200_handle;
@@ -231,6 +235,45 @@ int cge_b200_landmarks_aggregate(cge_b200_handle *h, int64_t n, int64_t d, int64
                                  double *out_embed, double *out_lweight, double *out_dii,
                                  int64_t *out_cluster, int64_t *out_edge_src, int64_t *out_edge_dst,
                                  double *out_eweights, int64_t edge_cap, int64_t *out_n_edges);
+
+/* SURVEY.md 8(f) F4 -- landmark SELECTION on the device.  Replaces runsplit(embedding, w, initial_clusters,
+ * n, s, rule) (landmarks.jl:279-345, called at :379) with the split rules split_cluster_rss (:155-210),
+ * split_cluster_size (:218-238) and split_cluster_diameter (:247-267): the embedding, the weights and the
+ * member order of every cluster stay in HBM; each cut runs its O(s d^2) / O(s d) passes (weighted moments and
+ * RSS, covariance, projection on the principal axis, sort, range moments, stable regrouping) as kernels and
+ * leaves the queue (landmarks.jl:12-46), the principal axis of the d x d covariance and the rule's
+ * comparisons to the host.
+ *   clusters      CSR: cluster c holds cluster_members[cluster_ptr[c] .. cluster_ptr[c+1]) (index_base-based
+ *                 vertex ids), clusters in the order of the reference's sort(initial_clusters)
+ *   land, forced  number of landmarks wanted / pieces every initial cluster is first cut into (n, s)
+ *   rule          CGE_B200_RULE_RSS (0), _SIZE (2), _DIAMETER (3); split_cluster_rss2 ("retained for testing
+ *                 purposes", :83-147) is not offered: CGE_B200_ERR_ARG
+ *   out_group     n entries: 0-based landmark id per vertex (runsplit's return value)
+ *   out_cuts      optional: number of cluster cuts performed
+ * The reference's ErrorExceptions ("Trying to split homogenous cluster", "Unexpected empty cluster generated")
+ * come back as CGE_B200_ERR_STATE with that text.
+ *   eig, eig_user optional callback for the one step the reference gives to LAPACK: the principal axis of a
+ *                 cluster's d x d weighted covariance (eigvecs(...)[:, end], landmarks.jl:160-162).  c is the
+ *                 full symmetric matrix, row-major; the callback writes the eigenvector of the largest
+ *                 eigenvalue to v (any length) and returns 0.  A cut depends on the SIGN LAPACK happens to
+ *                 return (which child is "low", where the median of an odd cluster goes), so a host that
+ *                 wants the reference's very landmarks passes its own LAPACK here (Julia: eigvecs, Python:
+ *                 numpy.linalg.eigh).  NULL: the library's own solver (Householder tridiagonalisation,
+ *                 bisection, inverse iteration), sign fixed to "largest-magnitude component positive". */
+#define CGE_B200_RULE_RSS 0
+#define CGE_B200_RULE_SIZE 2
+#define CGE_B200_RULE_DIAMETER 3
+typedef int (*cge_b200_eigvec_fn)(const double *c, int64_t d, double *v, void *user);
+int cge_b200_landmarks_select(cge_b200_handle *h, int64_t n, int64_t d, const double *embed,
+                              int64_t embed_row_stride, int64_t embed_col_stride, const double *vweights,
+                              int64_t n_clusters, const int64_t *cluster_ptr, const int64_t *cluster_members,
+                              int32_t index_base, int64_t land, int64_t forced, int32_t rule,
+                              cge_b200_eigvec_fn eig, void *eig_user, int64_t *out_group, int64_t *out_cuts);
+
+/* Host-only helper of the above, exported for its unit test: unit-length eigenvector of the largest
+ * eigenvalue of the symmetric d x d matrix a (row-major, upper triangle read), largest-magnitude component
+ * positive; *lambda (optional) receives the eigenvalue. */
+int cge_b200_sym_top_eigvec(const double *a, int64_t d, double *v_out, double *lambda);
 
 /* SURVEY.md 8(f) F3 -- ingest of the whitespace-delimited numeric tables the reference reads with
  * readdlm(fn, Float64 | Int) (auxilary.jl:86 edgelist, :123 communities, :150-155 embedding), parsed

@@ -182,7 +182,7 @@ def main():
     line = {
         "config": args.config, "workload": c["name"], "n_gpus": world, "n_scored": int(n_scored),
         "result": [float(x) for x in out], "alphas": int(st.n_alpha_run),
-        "fp_passes": int(st.fp_sweeps), "b_passes": int(st.b_sweeps),
+        "fp_passes": int(st.fp_sweeps), "b_passes": int(st.b_sweeps), "b_fused": int(st.b_fused),
         "driver": int(st.driver), "regime": int(st.regime),
         "iters": [int(x) for x in list(st.iters)[: int(st.n_alpha_run)]],
         "div": [float(x) for x in list(st.div)[: int(st.n_alpha_run)]],

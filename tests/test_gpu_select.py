@@ -1,0 +1,111 @@
+"""landmark selection (``runsplit`` + the split rules, landmarks.jl:155-345) on the
+device (``cge_b200_landmarks_select``) against the host mirror of the reference
+(``cge_jl_b200.landmarks.runsplit``).  The vertex -> landmark assignment is index work: the bar is
+equality, label by label -- with the d x d eigenproblem handed to the same LAPACK routine the mirror
+calls (the callback), and with the library's own solver against the mirror run under the same sign
+convention."""
+import numpy as np
+import pytest
+
+from cge_jl_b200 import divergence as dv
+from cge_jl_b200 import landmarks as lm_mod
+from cge_jl_b200.landmarks import (landmarks, runsplit, split_cluster_diameter, split_cluster_rss,
+                                   split_cluster_size)
+from util import clusters_of, load_fixture, planted_partition
+
+pytestmark = pytest.mark.gpu
+
+RULES = {"rss": split_cluster_rss, "size": split_cluster_size, "diameter": split_cluster_diameter}
+
+
+def _mirror(emb, vw, clusters, land, forced, rule, canonical):
+    old = lm_mod.CANONICAL_SIGN
+    lm_mod.CANONICAL_SIGN = canonical
+    try:
+        return runsplit(emb, vw, clusters, land, forced, RULES[rule])
+    finally:
+        lm_mod.CANONICAL_SIGN = old
+
+
+@pytest.mark.parametrize("rule", ["rss", "size", "diameter"])
+@pytest.mark.parametrize("n,k,d,land,forced", [(115, 0, 0, 20, 1), (115, 0, 0, 40, 4),
+                                               (3000, 7, 33, 150, 4), (20000, 16, 128, 400, 4)])
+def test_device_selection_equals_the_host_mirror(scorer, n, k, d, land, forced, rule):
+    if k == 0:
+        edges, ew, vw, comm, emb = load_fixture("test115_weighted.npz")
+    else:
+        edges, ew, vw, comm, emb = planted_partition(n, k, d, seed=n + land, weighted=True)
+    clusters = clusters_of(comm)
+    # the host's LAPACK through the callback: the mirror's own eigenvectors, signs included
+    group, cuts = scorer.landmarks_select(emb, vw, clusters, land, forced, rule, eig="lapack")
+    ref = _mirror(emb, vw, clusters, land, forced, rule, canonical=False)
+    assert group.min() == 0 and group.max() == land - 1 and cuts >= 1
+    assert np.array_equal(group, ref), f"{int((group != ref).sum())} of {n} vertices differ"
+    # the library's own eigen-solver, against the mirror under the same sign convention
+    group_b, _ = scorer.landmarks_select(emb, vw, clusters, land, forced, rule, eig="builtin")
+    ref_b = _mirror(emb, vw, clusters, land, forced, rule, canonical=True)
+    assert np.array_equal(group_b, ref_b), f"{int((group_b != ref_b).sum())} of {n} vertices differ"
+    # column-major embedding (what Julia passes)
+    group_f, _ = scorer.landmarks_select(np.asfortranarray(emb), vw, clusters, land, forced, rule)
+    assert np.array_equal(group_f, group)
+
+
+@pytest.mark.parametrize("rule", ["rss", "size", "diameter"])
+def test_duplicate_rows_and_small_clusters(scorer, rule):
+    """Exact ties in the projection (duplicated embedding rows, also at the extremes), clusters of one,
+    two and three vertices, clusters not larger than `forced`."""
+    rng = np.random.default_rng(5)
+    n, d = 400, 6
+    emb = rng.normal(size=(n, d))
+    emb[10:14] = emb[10]          # four identical rows
+    emb[200] = emb[201] = 50.0    # a duplicated extreme row
+    emb[300] = emb[301] = -50.0
+    vw = rng.uniform(0.5, 3.0, size=n)
+    sizes = [1, 2, 3, 4, 90, 100, 200]
+    perm = rng.permutation(n) + 1
+    clusters, o = [], 0
+    for s in sizes:
+        clusters.append(np.sort(perm[o:o + s]))
+        o += s
+    for land, forced in [(60, 4), (120, 2)]:
+        group, _ = scorer.landmarks_select(emb, vw, clusters, land, forced, rule)
+        ref = _mirror(emb, vw, clusters, land, forced, rule, canonical=False)
+        assert np.array_equal(group, ref)
+
+
+def test_reference_errors_come_back(scorer):
+    emb = np.ones((50, 4))
+    vw = np.ones(50)
+    with pytest.raises(RuntimeError, match="homogenous"):
+        scorer.landmarks_select(emb, vw, [np.arange(1, 51)], 5, 1, "rss")
+    with pytest.raises(RuntimeError):  # clusters that do not cover every vertex
+        scorer.landmarks_select(emb, vw, [np.arange(1, 40)], 5, 1, "rss")
+
+
+def test_selection_is_reproducible_and_feeds_landmarks(scorer):
+    """Two runs give the same assignment; landmarks(..., device=scorer) -- selection and aggregation on
+    the GPU -- equals landmarks(...) on the host, for every rule."""
+    edges, ew, vw, comm, emb = planted_partition(5000, 9, 24, seed=11, weighted=True)
+    clusters = clusters_of(comm)
+    a, _ = scorer.landmarks_select(emb, vw, clusters, 300, 4, "rss", eig="builtin")
+    b, _ = scorer.landmarks_select(emb, vw, clusters, 300, 4, "rss", eig="builtin")
+    assert np.array_equal(a, b)
+    for method in (split_cluster_rss, split_cluster_size, split_cluster_diameter):
+        args = (edges, ew, vw, clusters, comm, emb, False, 300, 4, method, False)
+        host, dev = landmarks(*args), landmarks(*args, device=scorer)
+        for x, y in zip(dev, host):
+            assert np.array_equal(x, y)
+
+
+def test_readme_golden_through_the_device_selection(scorer):
+    """The reference's README known answer (`-l 200 --seed 42` on the 10k example, README.md:99,
+    elements 1-2) with landmark selection, aggregation and scoring all on the GPU."""
+    edges, ew, vw, comm, emb = load_fixture("example10k.npz")
+    dii, lemb, lcomm, ledges, lw, lweight, v2l = landmarks(
+        edges, ew, vw, clusters_of(comm), comm, emb, False, 200, 4, split_cluster_rss, False,
+        device=scorer)
+    samples = dv.draw_samples(edges, ew, 10000, 1000, 42, False, False)
+    out = dv.wGCL(ledges, lw, lcomm, lemb, dii, lweight, vw, v2l, edges, ew, emb, False, 42, 1000,
+                  False, samples=samples, scorer=scorer)
+    assert out[0] == 6.25
+    assert abs(out[1] - 0.002961243353776198) <= 1e-9 * 0.002961243353776198

@@ -171,3 +171,33 @@ def test_diameter_filter_error_bound():
         E = 1e-3 * rmax2
         i, j = np.unravel_index(np.argmax(exact), exact.shape)
         assert approx[i, j] >= approx.max() - 2 * E
+
+
+def test_builtin_principal_axis_matches_lapack():
+    """cge_b200_sym_top_eigvec (the host-only eigen-solver behind cge_b200_landmarks_select when no
+    LAPACK callback is given) against numpy.linalg.eigh on weighted covariance
+    matrices: same principal axis to rounding, sign fixed to 'largest component positive'."""
+    import ctypes as C
+
+    from cge_jl_b200 import _lib
+
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for d in (1, 2, 3, 5, 16, 33, 64, 128):
+        for trial in range(4):
+            s = int(rng.integers(d + 2, 4 * d + 10))
+            y = rng.normal(size=(s, d)) * rng.uniform(0.1, 3.0, size=d)
+            if trial == 2:
+                y[:, 0] *= 1e3
+            if trial == 3 and d > 2:  # nearly rank one
+                y = y[:, :1] * rng.normal(size=d) + 1e-6 * y
+            a = y.T @ y
+            v, lam = np.zeros(d), C.c_double()
+            assert lib.cge_b200_sym_top_eigvec(a.ctypes.data_as(_lib._pd), d, v.ctypes.data_as(_lib._pd),
+                                               C.byref(lam)) == 0
+            w, vec = np.linalg.eigh(a)
+            ref = vec[:, -1] if vec[int(np.argmax(np.abs(vec[:, -1]))), -1] > 0 else -vec[:, -1]
+            gap = (w[-1] - w[-2]) / w[-1] if d > 1 else 1.0
+            assert abs(lam.value - w[-1]) <= 1e-13 * abs(w[-1])
+            assert np.abs(v - ref).max() * gap <= 1e-13
+            assert abs(np.linalg.norm(v) - 1.0) <= 1e-14 and v[int(np.argmax(np.abs(v)))] > 0
