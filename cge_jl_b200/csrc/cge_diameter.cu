@@ -108,7 +108,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 // One CTA (128 threads = 4 warps = the 128 TMEM lanes) per SM; strips of tiles of one tile row are
 // claimed from a counter.  Thread 0 is the TMA producer and the MMA issuer; all four warps are the
-// epilogue (thread t owns accumulator row t).
+// epilogue (thread t owns accumulator row t).  TWO accumulators in TMEM (2 x 128 columns): the 24 MMAs
+// of tile i+1 are issued before the epilogue of tile i starts, so the tensor pipe works through them
+// while the four warps read tile i's accumulator back (tcgen05.ld) and take its maximum.
+constexpr uint32_t DM_TMEM_COLS = 256;
 __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_constant__ DiamArgs a) {
     extern __shared__ __align__(1024) unsigned char sm[];
     const uint32_t opb = (uint32_t)a.ksteps * 4096u;
@@ -116,21 +119,21 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
     unsigned char *sB = sm + 2 * opb;             // two buffers of (hi, lo)
     float *nA = reinterpret_cast<float *>(sm + 6 * (size_t)opb);
     float *nB = nA + TILE;                        // [2][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nB + 2 * TILE);  // a_full, b_full[2], mma_done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nB + 2 * TILE);  // a_full, b_full[2], mma_done[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
     int *s_strip = reinterpret_cast<int *>(tmem_slot + 1);         // bi, bj0, count, first tile
     float *s_red = reinterpret_cast<float *>(s_strip + 4);         // [4]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint64_t *a_full = bars, *b_full = bars + 1, *mma_done = bars + 3;
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+        for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
         __syncwarp();
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                          smem_u32(tmem_slot)),
-                     "r"(128u)
+                     "r"(DM_TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -142,7 +145,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
     // (N>>3 at [17,23)), M = 128 (M>>4 at [24,29))
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t pol = l2_policy(true);  // blocks are re-read by many CTAs: keep them in L2
-    uint32_t ph_a = 0, ph_b0 = 0, ph_b1 = 0, ph_m = 0;
+    uint32_t ph_a = 0, ph_b = 0, ph_m = 0;  // ph_b / ph_m: one phase bit per buffer
     float lmax = 0.0f;
     const size_t blk_bytes = 2 * (size_t)opb;
     while (true) {
@@ -155,53 +158,59 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
         __syncthreads();
         const int bi = s_strip[0], bj0 = s_strip[1], cnt = s_strip[2], t0 = s_strip[3];
         if (bi < 0) break;
+        // thread 0: wait for tile i's column block, issue its MMAs into accumulator i & 1
+        auto issue = [&](int i) {
+            const int buf = i & 1;
+            if (i == 0) {
+                mbar_wait(a_full, ph_a);
+                ph_a ^= 1u;
+            }
+            mbar_wait(b_full + buf, (ph_b >> buf) & 1u);
+            ph_b ^= 1u << buf;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + opb;
+            const uint32_t b_hi = smem_u32(sB + (size_t)buf * blk_bytes), b_lo = b_hi + opb;
+            const uint32_t acc_addr = tmem + (uint32_t)buf * 128u;
+            uint32_t acc = 0;
+            // Gram tile = hi.hi + hi.lo + lo.hi ; K step s covers k-chunks 2s, 2s+1
+            for (int term = 0; term < 3; ++term) {
+                const uint32_t pa = term == 2 ? a_lo : a_hi, pb = term == 1 ? b_lo : b_hi;
+                for (int s = 0; s < a.ksteps; ++s) {
+                    umma_bf16(acc_addr, umma_desc(pa + (uint32_t)s * 4096u, 2048u, 128u),
+                              umma_desc(pb + (uint32_t)s * 4096u, 2048u, 128u), idesc, acc);
+                    acc = 1;
+                }
+            }
+            umma_commit(mma_done + buf);
+        };
+        auto request_b = [&](int i) {  // column block of tile i into buffer i & 1 (its last reader is done)
+            const int buf = i & 1;
+            mbar_expect_tx(b_full + buf, 2 * opb);
+            bulk_g2s(sB + (size_t)buf * blk_bytes, a.packed + (size_t)(bj0 + i) * blk_bytes, 2 * opb,
+                     b_full + buf, pol);
+        };
         if (tid == 0) {
+            // every MMA of the previous strip has completed (its last mma_done was waited for), so the
+            // row block and both column buffers are free
             mbar_expect_tx(a_full, 2 * opb);
             bulk_g2s(sA, a.packed + (size_t)bi * blk_bytes, 2 * opb, a_full, pol);
-            mbar_expect_tx(b_full, 2 * opb);
-            bulk_g2s(sB, a.packed + (size_t)bj0 * blk_bytes, 2 * opb, b_full, pol);
+            request_b(0);
+            if (cnt > 1) request_b(1);
         }
         nA[tid] = a.norms[(size_t)bi * TILE + tid];
         nB[tid] = a.norms[(size_t)bj0 * TILE + tid];
         __syncthreads();  // also: every thread has read s_strip
+        if (tid == 0) issue(0);
         for (int i = 0; i < cnt; ++i) {
             const int buf = i & 1;
-            if (tid == 0) {
-                if (i + 1 < cnt) {  // the other buffer was last read by tile i-1's MMAs: complete
-                    mbar_expect_tx(b_full + (buf ^ 1), 2 * opb);
-                    bulk_g2s(sB + (size_t)(buf ^ 1) * blk_bytes,
-                             a.packed + (size_t)(bj0 + i + 1) * blk_bytes, 2 * opb,
-                             b_full + (buf ^ 1), pol);
-                }
-                if (i == 0) {
-                    mbar_wait(a_full, ph_a);
-                    ph_a ^= 1u;
-                }
-                if (buf == 0) {
-                    mbar_wait(b_full, ph_b0);
-                    ph_b0 ^= 1u;
-                } else {
-                    mbar_wait(b_full + 1, ph_b1);
-                    ph_b1 ^= 1u;
-                }
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + opb;
-                const uint32_t b_hi = smem_u32(sB + (size_t)buf * blk_bytes), b_lo = b_hi + opb;
-                uint32_t acc = 0;
-                // Gram tile = hi.hi + hi.lo + lo.hi ; K step s covers k-chunks 2s, 2s+1
-                for (int term = 0; term < 3; ++term) {
-                    const uint32_t pa = term == 2 ? a_lo : a_hi, pb = term == 1 ? b_lo : b_hi;
-                    for (int s = 0; s < a.ksteps; ++s) {
-                        umma_bf16(tmem, umma_desc(pa + (uint32_t)s * 4096u, 2048u, 128u),
-                                  umma_desc(pb + (uint32_t)s * 4096u, 2048u, 128u), idesc, acc);
-                        acc = 1;
-                    }
-                }
-                umma_commit(mma_done);
-            }
+            // the other accumulator was read by the epilogue of tile i-1, which ended at the barrier
+            // below: tile i+1's MMAs may start while this tile's accumulator is read back
+            if (tid == 0 && i + 1 < cnt) issue(i + 1);
             if (i + 1 < cnt) nB[(buf ^ 1) * TILE + tid] = a.norms[(size_t)(bj0 + i + 1) * TILE + tid];
-            mbar_wait(mma_done, ph_m);
-            ph_m ^= 1u;
+            mbar_wait(mma_done + buf, (ph_m >> buf) & 1u);
+            ph_m ^= 1u << buf;
+            // tile i's MMAs are complete: its column buffer can take the block of tile i+2
+            if (tid == 0 && i + 2 < cnt) request_b(i + 2);
             __syncwarp();  // lane 0 of warp 0 rejoins before the warp-collective TMEM loads
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // epilogue: thread tid owns accumulator row tid (TMEM lane), 128 FP32 columns
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
 #pragma unroll
             for (int c0 = 0; c0 < TILE; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128 + c0), v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) best = fmaxf(best, fmaf(-2.0f, v[j], nb_[c0 + j]));
             }
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
             for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, off));
             if (lane == 0) s_red[warp] = best;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();  // TMEM reads done before the next tile's MMAs overwrite the accumulator
+            __syncthreads();  // this accumulator's reads are done before tile i+2's MMAs overwrite it
             if (tid == 0) {
                 const float m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
                 a.tile_max[(size_t)t0 + i] = m;
@@ -231,7 +240,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
     __syncthreads();
     if (warp == 0) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(DM_TMEM_COLS)
                      : "memory");
     }
 }

@@ -17,8 +17,6 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include <type_traits>
-
 namespace cge {
 
 constexpr int TILE = 128;
@@ -190,83 +188,6 @@ __device__ __forceinline__ double2 ld_stream(const double2 *p, uint64_t pol) {
     return v;
 }
 
-// Rows of a tile travel in batches of four (4 KB per warp) through two register buffers: while one
-// batch is consumed the next is in flight.  The buffers are carried ACROSS tiles: the last batch of
-// a tile requests the first batch of the CTA's next tile, so the reductions, shared-memory column
-// sums, barrier and (B sweep) atomics at the end of a tile run with loads outstanding instead of
-// draining the memory pipeline once per tile.  XNB is even: a tile starts and its successor's first
-// batch lands in buffer 0.
-#ifndef CGE_XTILE
-#define CGE_XTILE 1
-#endif
-constexpr int XBR = 4, XNB = ROWS_PER_WARP / XBR;
-static_assert(XNB % 2 == 0, "a tile must end on buffer 1");
-struct RowBuf {
-    double2 v01[2][XBR], v23[2][XBR];
-};
-template <int BUF>
-__device__ __forceinline__ void load_rows(RowBuf &rb, const double *__restrict__ qt, int batch,
-                                          uint64_t pol) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const double2 *base =
-        reinterpret_cast<const double2 *>(qt + (size_t)(w * ROWS_PER_WARP + batch * XBR) * TILE);
-#pragma unroll
-    for (int r = 0; r < XBR; ++r) {
-        rb.v01[BUF][r] = ld_stream(base + r * (TILE / 2) + lane, pol);
-        rb.v23[BUF][r] = ld_stream(base + r * (TILE / 2) + 32 + lane, pol);
-    }
-}
-// request what follows batch `batch` of tile qt: its next batch, or batch 0 of the next tile
-template <int BATCH>
-__device__ __forceinline__ void load_ahead(RowBuf &rb, const double *__restrict__ qt, uint64_t pol,
-                                           const double *__restrict__ qnext, uint64_t pol_next) {
-    if constexpr (BATCH + 1 < XNB) {
-        load_rows<(BATCH + 1) & 1>(rb, qt, BATCH + 1, pol);
-    } else {
-        if (qnext) load_rows<0>(rb, qnext, 0, pol_next);
-    }
-}
-// walks the tiles t = first, first + stride, ... < a.tile_end of a CTA with the carried buffers
-struct TileWalk {
-    long long t, stride;
-    const double *qt, *qnext;
-    uint64_t pol, pol_next;
-    template <class A>
-    __device__ __forceinline__ TileWalk(const A &a, RowBuf &rb) : t(a.tile_begin + blockIdx.x), stride(gridDim.x) {
-        qt = qnext = nullptr;
-        pol = pol_next = 0;
-        if (t < a.tile_end) {
-            qnext = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
-            pol_next = l2_policy_for(t - a.tile_begin, a.resident_tiles);
-            load_rows<0>(rb, qnext, 0, pol_next);
-        }
-    }
-    // makes tile t current and looks up its successor; false when the CTA has no tile left
-    template <class A>
-    __device__ __forceinline__ bool next(const A &a, bool first) {
-        if (!first) t += stride;
-        if (t >= a.tile_end) return false;
-        qt = qnext;
-        pol = pol_next;
-        const long long tn = t + stride;
-        if (tn < a.tile_end) {
-            qnext = a.q + (size_t)(tn - a.tile_begin) * TILE_ELEMS;
-            pol_next = l2_policy_for(tn - a.tile_begin, a.resident_tiles);
-        } else {
-            qnext = nullptr;
-        }
-        return true;
-    }
-};
-
-template <int I, int N, class F>
-__device__ __forceinline__ void static_for(F &&f) {
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
-
 // Reduce NV per-lane values across the 32 lanes of a warp with NV-1 + (5 - log2 NV) shuffle
 // steps instead of 5*NV.  On return v[0] holds the warp total of value index
 // treduce_index<NV>(lane); the summation tree is fixed.
@@ -337,54 +258,6 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
         c2 = fma(ti, g2, c2);
         c3 = fma(ti, g3, c3);
     }
-    warp_treduce<ROWS_PER_WARP>(racc, lane);
-    if ((lane & 1) == 0)
-        a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + treduce_index<16>(lane)] = racc[0];
-    const bool offdiag = bi != bj;
-    if (offdiag) {
-        double2 *sc = reinterpret_cast<double2 *>(s_col + w * TILE);
-        sc[lane] = make_double2(c0, c1);
-        sc[32 + lane] = make_double2(c2, c3);
-    }
-    __syncthreads();
-    if (offdiag && threadIdx.x < TILE) {
-        double s = 0.0;
-#pragma unroll
-        for (int w2 = 0; w2 < NWARPS; ++w2) s += s_col[w2 * TILE + threadIdx.x];
-        a.partA[(size_t)bi * a.np + (size_t)bj * TILE + threadIdx.x] = s;
-    }
-}
-
-// the same pass with the carried row buffers (see RowBuf): identical arithmetic, row by row
-template <int M>
-__device__ __forceinline__ void tile_pass_u_x(RowBuf &rb, const TileWalk &tw, int bi, int bj,
-                                              const SweepArgs &a, double *s_col) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int row0 = w * ROWS_PER_WARP;
-    const double *Tc = a.Ta + (size_t)bj * TILE;
-    const double2 tc01 = __ldcg(reinterpret_cast<const double2 *>(Tc) + lane);
-    const double2 tc23 = __ldcg(reinterpret_cast<const double2 *>(Tc + 64) + lane);
-    const double trow =
-        lane < ROWS_PER_WARP ? __ldcg(a.Ta + (size_t)bi * TILE + row0 + lane) : 0.0;
-    double racc[ROWS_PER_WARP];
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-    static_for<0, XNB>([&](auto B_) {
-        constexpr int batch = decltype(B_)::value, cb = batch & 1;
-        load_ahead<batch>(rb, tw.qt, tw.pol, tw.qnext, tw.pol_next);
-#pragma unroll
-        for (int r4 = 0; r4 < XBR; ++r4) {
-            const int rr = batch * XBR + r4;
-            const double2 v01 = rb.v01[cb][r4], v23 = rb.v23[cb][r4];
-            const double ti = __shfl_sync(FULL, trow, rr);
-            const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
-            const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
-            racc[rr] = fma(g3, tc23.y, fma(g2, tc23.x, fma(g1, tc01.y, g0 * tc01.x)));
-            c0 = fma(ti, g0, c0);
-            c1 = fma(ti, g1, c1);
-            c2 = fma(ti, g2, c2);
-            c3 = fma(ti, g3, c3);
-        }
-    });
     warp_treduce<ROWS_PER_WARP>(racc, lane);
     if ((lane & 1) == 0)
         a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + treduce_index<16>(lane)] = racc[0];
@@ -476,75 +349,6 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
             a.partB[o] = rout[0];
         }
     }
-    const bool offdiag = bi != bj;
-    if (offdiag) {
-        double2 *sa = reinterpret_cast<double2 *>(s_col + w * TILE);
-        double2 *sb = reinterpret_cast<double2 *>(s_col + NWARPS * TILE + w * TILE);
-        sa[lane] = make_double2(ci0, ci1);
-        sa[32 + lane] = make_double2(ci2, ci3);
-        sb[lane] = make_double2(co0, co1);
-        sb[32 + lane] = make_double2(co2, co3);
-    }
-    __syncthreads();
-    if (offdiag) {
-        const int c = threadIdx.x & (TILE - 1);
-        const double *src = s_col + (threadIdx.x >> 7) * NWARPS * TILE;
-        double s = 0.0;
-#pragma unroll
-        for (int w2 = 0; w2 < NWARPS; ++w2) s += src[w2 * TILE + c];
-        double *dst = (threadIdx.x >> 7) ? a.partB : a.partA;
-        dst[(size_t)bi * a.np + (size_t)bj * TILE + c] = s;
-    }
-}
-
-// the same pass with the row buffers carried across tiles (see RowBuf): identical arithmetic
-template <int M>
-__device__ __forceinline__ void tile_pass_d_x(RowBuf &rb, const TileWalk &tw, int bi, int bj,
-                                              const SweepArgs &a, double *s_col) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int row0 = w * ROWS_PER_WARP;
-    const double *Tic = a.Ta + (size_t)bj * TILE, *Toc = a.Tb + (size_t)bj * TILE;
-    const double2 ti01 = __ldcg(reinterpret_cast<const double2 *>(Tic) + lane);
-    const double2 ti23 = __ldcg(reinterpret_cast<const double2 *>(Tic + 64) + lane);
-    const double2 to01 = __ldcg(reinterpret_cast<const double2 *>(Toc) + lane);
-    const double2 to23 = __ldcg(reinterpret_cast<const double2 *>(Toc + 64) + lane);
-    const bool ld = lane < ROWS_PER_WARP;
-    const double trow_in = ld ? __ldcg(a.Ta + (size_t)bi * TILE + row0 + lane) : 0.0;
-    const double trow_out = ld ? __ldcg(a.Tb + (size_t)bi * TILE + row0 + lane) : 0.0;
-    double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0;  // Sin column sums  (Tout_r * g)
-    double co0 = 0.0, co1 = 0.0, co2 = 0.0, co3 = 0.0;  // Sout column sums (Tin_r * g)
-    static_for<0, XNB>([&](auto B_) {
-        constexpr int batch = decltype(B_)::value, cb = batch & 1;
-        load_ahead<batch>(rb, tw.qt, tw.pol, tw.qnext, tw.pol_next);
-        double rin[XBR], rout[XBR];
-#pragma unroll
-        for (int r4 = 0; r4 < XBR; ++r4) {
-            const int rr = batch * XBR + r4;
-            const double2 v01 = rb.v01[cb][r4], v23 = rb.v23[cb][r4];
-            const double t_in = __shfl_sync(FULL, trow_in, rr);
-            const double t_out = __shfl_sync(FULL, trow_out, rr);
-            const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
-            const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
-            rin[r4] = fma(g3, to23.y, fma(g2, to23.x, fma(g1, to01.y, g0 * to01.x)));
-            rout[r4] = fma(g3, ti23.y, fma(g2, ti23.x, fma(g1, ti01.y, g0 * ti01.x)));
-            ci0 = fma(t_out, g0, ci0);
-            ci1 = fma(t_out, g1, ci1);
-            ci2 = fma(t_out, g2, ci2);
-            ci3 = fma(t_out, g3, ci3);
-            co0 = fma(t_in, g0, co0);
-            co1 = fma(t_in, g1, co1);
-            co2 = fma(t_in, g2, co2);
-            co3 = fma(t_in, g3, co3);
-        }
-        warp_treduce<XBR>(rin, lane);
-        warp_treduce<XBR>(rout, lane);
-        if ((lane & 7) == 0) {
-            const size_t o = (size_t)bj * a.np + (size_t)bi * TILE + row0 + batch * XBR +
-                             treduce_index<XBR>(lane);
-            a.partA[o] = rin[0];
-            a.partB[o] = rout[0];
-        }
-    });
     const bool offdiag = bi != bj;
     if (offdiag) {
         double2 *sa = reinterpret_cast<double2 *>(s_col + w * TILE);
@@ -694,88 +498,6 @@ __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi
     flush(cur);
 }
 
-// the same sweep with the row buffers carried across tiles (see RowBuf)
-template <int M, bool DIRECTED>
-__device__ __forceinline__ void tile_bpass_x(RowBuf &rb, const TileWalk &tw, int bi, int bj,
-                                             const SweepArgs &a) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int row0 = w * ROWS_PER_WARP;
-    const int gc0 = bj * TILE + 2 * lane, gc2 = bj * TILE + 64 + 2 * lane;
-    const int2 cc01 = __ldcg(reinterpret_cast<const int2 *>(a.comm + gc0));
-    const int2 cc23 = __ldcg(reinterpret_cast<const int2 *>(a.comm + gc2));
-    const int cc[4] = {cc01.x, cc01.y, cc23.x, cc23.y};
-    const int gc[4] = {gc0, gc0 + 1, gc2, gc2 + 1};
-    // column factors: undirected T_c; directed Tin_c (for B[cr][cc]) and Tout_c (for B[cc][cr])
-    const double2 ta01 = __ldcg(reinterpret_cast<const double2 *>(a.Ta + gc0));
-    const double2 ta23 = __ldcg(reinterpret_cast<const double2 *>(a.Ta + gc2));
-    const double tca[4] = {ta01.x, ta01.y, ta23.x, ta23.y};
-    double tcb[4] = {0.0, 0.0, 0.0, 0.0};
-    if (DIRECTED) {
-        const double2 tb01 = __ldcg(reinterpret_cast<const double2 *>(a.Tb + gc0));
-        const double2 tb23 = __ldcg(reinterpret_cast<const double2 *>(a.Tb + gc2));
-        tcb[0] = tb01.x; tcb[1] = tb01.y; tcb[2] = tb23.x; tcb[3] = tb23.y;
-    }
-    const bool ld = lane < ROWS_PER_WARP;
-    const int grow = bi * TILE + row0 + lane;
-    const int crow = ld ? __ldcg(a.comm + grow) : -1;
-    // row factors: undirected T_r; directed Tout_r (rowA) and Tin_r (rowB)
-    const double trow_a = ld ? __ldcg((DIRECTED ? a.Tb : a.Ta) + grow) : 0.0;
-    const double trow_b = (DIRECTED && ld) ? __ldcg(a.Ta + grow) : 0.0;
-    const bool diag = bi == bj;
-    double accA[4] = {0.0, 0.0, 0.0, 0.0}, accB[4] = {0.0, 0.0, 0.0, 0.0};
-    int cur = __shfl_sync(FULL, crow, 0);
-
-    auto flush = [&](int cr) {
-        if (cr >= 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                // B[cr][cc] += (sum_r rowA_r g) * colA_c
-                flush_bins(accA[k] * tca[k], cc[k], (long long)cr * a.k, 1, a.B, lane);
-                if (DIRECTED && !diag)  // B[cc][cr] += (sum_r Tin_r g) * Tout_c
-                    flush_bins(accB[k] * tcb[k], cc[k], (long long)cr, a.k, a.B, lane);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) accA[k] = accB[k] = 0.0;
-    };
-
-    // rows in batches of four through the carried buffers; a batch whose rows all share the current
-    // row community (the common case after the community sort) runs without any per-row check
-    static_for<0, XNB>([&](auto B_) {
-        constexpr int batch = decltype(B_)::value, cb = batch & 1;
-        load_ahead<batch>(rb, tw.qt, tw.pol, tw.qnext, tw.pol_next);
-        const unsigned bm = ((1u << XBR) - 1u) << (batch * XBR);
-        const bool uniform = (__ballot_sync(FULL, crow != cur) & bm) == 0u;
-#pragma unroll
-        for (int r8 = 0; r8 < XBR; ++r8) {
-            const int rr = batch * XBR + r8;
-            if (!uniform) {
-                const int cr = __shfl_sync(FULL, crow, rr);
-                if (cr != cur) {  // warp-uniform
-                    flush(cur);
-                    cur = cr;
-                }
-            }
-            double g[4] = {powm_any<M>(rb.v01[cb][r8].x, a.m), powm_any<M>(rb.v01[cb][r8].y, a.m),
-                           powm_any<M>(rb.v23[cb][r8].x, a.m), powm_any<M>(rb.v23[cb][r8].y, a.m)};
-            if (!DIRECTED && diag) {  // unordered pairs once: keep col >= row (divergence.jl:229-230)
-                const int gr = bi * TILE + row0 + rr;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) g[k] = gc[k] >= gr ? g[k] : 0.0;
-            }
-            const double ra = __shfl_sync(FULL, trow_a, rr);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) accA[k] = fma(ra, g[k], accA[k]);
-            if (DIRECTED) {
-                const double rb = __shfl_sync(FULL, trow_b, rr);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) accB[k] = fma(rb, g[k], accB[k]);
-            }
-        }
-    });
-    flush(cur);
-}
-
 // ---------------------------------------------------------------------------------------------
 // Fused pass (undirected): B sweep of alpha = (M-1)/4 + FIRST fixed-point pass of alpha = M/4.
 // T is warm-started (divergence.jl:33, 139-168: the T an alpha starts from is the T the previous
@@ -785,9 +507,12 @@ __device__ __forceinline__ void tile_bpass_x(RowBuf &rb, const TileWalk &tw, int
 // tile_pass_u's operation for operation (same FMA chains, same reduction trees: bit-identical
 // partial slots), the bin arithmetic is tile_bpass<M-1>'s.
 // ---------------------------------------------------------------------------------------------
+#ifndef CGE_UB_ROWS
+#define CGE_UB_ROWS 4  // rows requested together in the fused pass (measured r02, config 4: 4 -> 29.31 s per run, 8 -> 29.36, 16 -> 29.74)
+#endif
 template <int M>
-__device__ __forceinline__ void tile_pass_ub(RowBuf &rb, const TileWalk &tw, int bi, int bj,
-                                             const SweepArgs &a, double *s_col) {
+__device__ __forceinline__ void tile_pass_ub(const double *__restrict__ qt, int bi, int bj,
+                                             const SweepArgs &a, double *s_col, uint64_t pol) {
     static_assert(M >= 2, "the fused pass needs a previous alpha");
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int row0 = w * ROWS_PER_WARP;
@@ -801,6 +526,7 @@ __device__ __forceinline__ void tile_pass_ub(RowBuf &rb, const TileWalk &tw, int
     const double trow = ld ? __ldcg(a.Ta + grow) : 0.0;
     const int crow = ld ? __ldcg(a.comm + grow) : -1;
     const bool diag = bi == bj;
+    const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
     double racc[ROWS_PER_WARP];
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;  // bins: sum_r T_r q^(M-1) per column
@@ -817,14 +543,20 @@ __device__ __forceinline__ void tile_pass_ub(RowBuf &rb, const TileWalk &tw, int
         b0 = b1 = b2 = b3 = 0.0;
     };
 
-    static_for<0, XNB>([&](auto B_) {
-        constexpr int batch = decltype(B_)::value, cb = batch & 1;
-        load_ahead<batch>(rb, tw.qt, tw.pol, tw.qnext, tw.pol_next);
-        const unsigned bm = ((1u << XBR) - 1u) << (batch * XBR);
+    constexpr int BR = CGE_UB_ROWS, NB = ROWS_PER_WARP / BR;
+#pragma unroll
+    for (int batch = 0; batch < NB; ++batch) {
+        double2 v01[BR], v23[BR];
+#pragma unroll
+        for (int r = 0; r < BR; ++r) {
+            v01[r] = ld_stream(base + (batch * BR + r) * (TILE / 2) + lane, pol);
+            v23[r] = ld_stream(base + (batch * BR + r) * (TILE / 2) + 32 + lane, pol);
+        }
+        const unsigned bm = ((1u << BR) - 1u) << (batch * BR);
         const bool uniform = (__ballot_sync(FULL, crow != cur) & bm) == 0u;
 #pragma unroll
-        for (int r4 = 0; r4 < XBR; ++r4) {
-            const int rr = batch * XBR + r4;
+        for (int r = 0; r < BR; ++r) {
+            const int rr = batch * BR + r;
             if (!uniform) {
                 const int cr = __shfl_sync(FULL, crow, rr);
                 if (cr != cur) {  // warp-uniform
@@ -832,7 +564,7 @@ __device__ __forceinline__ void tile_pass_ub(RowBuf &rb, const TileWalk &tw, int
                     cur = cr;
                 }
             }
-            const double q0 = rb.v01[cb][r4].x, q1 = rb.v01[cb][r4].y, q2 = rb.v23[cb][r4].x, q3 = rb.v23[cb][r4].y;
+            const double q0 = v01[r].x, q1 = v01[r].y, q2 = v23[r].x, q3 = v23[r].y;
             const double ti = __shfl_sync(FULL, trow, rr);
             // fixed-point pass, exponent M (as tile_pass_u)
             const double g0 = powm<M>(q0), g1 = powm<M>(q1), g2 = powm<M>(q2), g3 = powm<M>(q3);
@@ -855,7 +587,7 @@ __device__ __forceinline__ void tile_pass_ub(RowBuf &rb, const TileWalk &tw, int
             b2 = fma(ti, h2, b2);
             b3 = fma(ti, h3, b3);
         }
-    });
+    }
     flush(cur);
     warp_treduce<ROWS_PER_WARP>(racc, lane);
     if ((lane & 1) == 0)
@@ -881,18 +613,6 @@ template <int M, bool DIRECTED>
 __global__ void __launch_bounds__(NTHREADS, 2) k_sweep(const __grid_constant__ SweepArgs a) {
     __shared__ __align__(16) double s_col[2 * 2 * NWARPS * TILE];
     int it = 0;
-#if CGE_XTILE
-    RowBuf rb;
-    TileWalk tw(a, rb);
-    for (bool first = true; tw.next(a, first); first = false, ++it) {
-        const int2 ij = a.tile_ij[tw.t];
-        double *sc = s_col + (it & 1) * 2 * NWARPS * TILE;
-        if constexpr (DIRECTED)
-            tile_pass_d_x<M>(rb, tw, ij.x, ij.y, a, sc);
-        else
-            tile_pass_u_x<M>(rb, tw, ij.x, ij.y, a, sc);
-    }
-#else
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++it) {
         const int2 ij = a.tile_ij[t];
         const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
@@ -903,25 +623,15 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_sweep(const __grid_constant__ S
         else
             tile_pass_u<M>(qt, ij.x, ij.y, a, sc, pol);
     }
-#endif
 }
 
 template <int M, bool DIRECTED>
 __global__ void __launch_bounds__(NTHREADS, 2) k_bsweep(const __grid_constant__ SweepArgs a) {
-#if CGE_XTILE
-    RowBuf rb;
-    TileWalk tw(a, rb);
-    for (bool first = true; tw.next(a, first); first = false) {
-        const int2 ij = a.tile_ij[tw.t];
-        tile_bpass_x<M, DIRECTED>(rb, tw, ij.x, ij.y, a);
-    }
-#else
     for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x) {
         const int2 ij = a.tile_ij[t];
         tile_bpass<M, DIRECTED>(a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS, ij.x, ij.y, a,
                                 l2_policy_for(t - a.tile_begin, a.resident_tiles));
     }
-#endif
 }
 
 // B sweep of alpha (M-1)/4 fused with the first fixed-point pass of alpha M/4 (tile_pass_ub): fills
@@ -931,11 +641,11 @@ template <int M>
 __global__ void __launch_bounds__(NTHREADS, 2) k_bfp(const __grid_constant__ SweepArgs a) {
     __shared__ __align__(16) double s_col[2 * NWARPS * TILE];
     int it = 0;
-    RowBuf rb;
-    TileWalk tw(a, rb);
-    for (bool first = true; tw.next(a, first); first = false, ++it) {
-        const int2 ij = a.tile_ij[tw.t];
-        tile_pass_ub<M>(rb, tw, ij.x, ij.y, a, s_col + (it & 1) * NWARPS * TILE);
+    for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++it) {
+        const int2 ij = a.tile_ij[t];
+        tile_pass_ub<M>(a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS, ij.x, ij.y, a,
+                        s_col + (it & 1) * NWARPS * TILE,
+                        l2_policy_for(t - a.tile_begin, a.resident_tiles));
     }
 }
 template <int M>
@@ -998,18 +708,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
         // a global counter 70, this 66-67.
         // (pass 1 of an alpha whose partial slots k_bfp has just filled has no tile phase)
         if (!(it == 0 && a.skip_first_tiles)) {
-#if CGE_XTILE
-            RowBuf rb;
-            TileWalk tw(a, rb);
-            for (bool first = true; tw.next(a, first); first = false, ++tile_it) {
-                const int2 ij = a.tile_ij[tw.t];
-                double *sc = s_col + (tile_it & 1) * 2 * NWARPS * TILE;
-                if constexpr (DIRECTED)
-                    tile_pass_d_x<M>(rb, tw, ij.x, ij.y, a, sc);
-                else
-                    tile_pass_u_x<M>(rb, tw, ij.x, ij.y, a, sc);
-            }
-#else
             for (long long t = a.tile_begin + blockIdx.x; t < a.tile_end; t += gridDim.x, ++tile_it) {
                 const int2 ij = a.tile_ij[t];
                 const double *qt = a.q + (size_t)(t - a.tile_begin) * TILE_ELEMS;
@@ -1020,7 +718,6 @@ __global__ void __launch_bounds__(NTHREADS, 2) k_fixed_point(const __grid_consta
                 else
                     tile_pass_u<M>(qt, ij.x, ij.y, a, sc, pol);
             }
-#endif
         }
         clk.mark(0);  // tiles of block 0
         grid.sync();

@@ -80,6 +80,10 @@ def _w_mean(m, w):
 # selection (cge_b200_landmarks_select) does -- largest-magnitude component positive -- so that the two
 # can be compared label by label; the default keeps whatever LAPACK returns, like the reference.
 CANONICAL_SIGN = False
+# who answers the d x d eigenproblem of a cut when the selection runs on the device (landmarks(..., device=)):
+# "lapack" = numpy.linalg.eigh through the library's callback (this mirror's own routine), "builtin" = the
+# library's solver with the canonical sign
+DEVICE_EIG = "lapack"
 
 
 def _pc1(m, w):
@@ -269,7 +273,7 @@ def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land
     rule = {split_cluster_rss: "rss", split_cluster_size: "size",
             split_cluster_diameter: "diameter"}.get(method)
     if device is not None and rule is not None:  # the cuts run on the GPU
-        lm = device.landmarks_select(embedding, vweights, clusters, land, forced, rule)[0] + 1
+        lm = device.landmarks_select(embedding, vweights, clusters, land, forced, rule, eig=DEVICE_EIG)[0] + 1
     else:
         lm = runsplit(embedding, vweights, clusters, land, forced, method) + 1
     if verbose:

@@ -20,6 +20,7 @@ using CGE
 using CGE: parseargs, landmarks, louvain_clust   # re-exported unchanged; wGCL* are defined here
 using StatsBase
 using Random
+using LinearAlgebra: eigvecs
 
 export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table, landmarks_b200
 
@@ -155,11 +156,61 @@ function draw_samples(adj_edges::Array{Int,2}, adj_eweights::Vector{Float64}, ad
     return pos_i, pos_j, pos_w, neg_i, neg_j
 end
 
+# the one step of a cut the reference gives to LAPACK (landmarks.jl:160-162: eigvecs(yᵀwy)[:, end]), as the
+# callback of cge_b200_landmarks_select: the matrix arrives row-major = column-major (it is symmetric)
+function _principal_axis(c::Ptr{Float64}, d::Int64, v::Ptr{Float64}, ::Ptr{Cvoid})::Cint
+    try
+        A = unsafe_wrap(Array, c, (Int(d), Int(d)))
+        unsafe_copyto!(v, pointer(eigvecs(Matrix(A))[:, end]), Int(d))    # same call, same LAPACK, same sign
+        return Cint(0)
+    catch
+        return Cint(1)
+    end
+end
+
+const RULE_CODES = Dict{Function,Int32}(CGE.split_cluster_rss => 0, CGE.split_cluster_size => 2,
+                                        CGE.split_cluster_diameter => 3)
+
+"""
+    runsplit_b200(embedding, w, initial_clusters, n, s, rule)
+
+`CGE.runsplit` (src/landmarks.jl:279-345) with the cuts of the split rule on the device
+(`cge_b200_landmarks_select`, SURVEY.md 8(f) F4): the embedding and the member order of every cluster stay
+in HBM, the queue stays on the host, and the d x d eigenproblem of each cut is answered by Julia's own
+`eigvecs` through a callback, so the principal axis (and its sign) is the reference's.  `rule` is one of
+`split_cluster_rss`, `split_cluster_size`, `split_cluster_diameter`; anything else (`split_cluster_rss2`)
+falls back to `CGE.runsplit`.  Returns the 0-based group id per vertex like `runsplit`.
+"""
+function runsplit_b200(embedding::Array{Float64,2}, w::Vector{Float64}, initial_clusters::Vector{Vector{Int}},
+                       n::Int, s::Int, rule::Function)
+    haskey(RULE_CODES, rule) || return CGE.runsplit(embedding, w, initial_clusters, n, s, rule)
+    cl = sort(initial_clusters)                                               # landmarks.jl:281
+    ptr = Int64[0; cumsum(length.(cl))]
+    members = Int64.(reduce(vcat, cl))
+    rows, dim = size(embedding)
+    group = Vector{Int64}(undef, rows)
+    cb = @cfunction(_principal_axis, Cint, (Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Cvoid}))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cge_b200_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), 0, h))
+    try
+        GC.@preserve embedding w ptr members group begin
+            check(ccall((:cge_b200_landmarks_select, LIB), Cint,
+                        (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Int64},
+                         Ptr{Int64}, Int32, Int64, Int64, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}),
+                        h[], rows, dim, embedding, 1, rows,               # column-major: row stride 1
+                        w, length(cl), ptr, members, 1, n, s, RULE_CODES[rule], cb, C_NULL, group, C_NULL))
+        end
+    finally
+        ccall((:cge_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    return group
+end
+
 """
     landmarks_b200(edges, weights, vweights, clusters, comm, embedding, verbose, land, forced, method, directed)
 
-`CGE.landmarks` (src/landmarks.jl:365-465) with the aggregation after `runsplit` (:387-463) on the device
-(`cge_b200_landmarks_aggregate`, SURVEY.md 8(f) F2): selection stays in Julia, the centroids, weights, d_ii,
+`CGE.landmarks` (src/landmarks.jl:365-465) with `runsplit` (`runsplit_b200`, SURVEY.md 8(f) F4) and the
+aggregation after it (:387-463, `cge_b200_landmarks_aggregate`, SURVEY.md 8(f) F2) on the device: the centroids, weights, d_ii,
 landmark communities and the weighted landmark edge list come back bit-identical to the Julia loops.  Same
 arguments and return tuple as `landmarks`; pass it to `wGCL` unchanged.
 """
@@ -172,7 +223,7 @@ function landmarks_b200(edges::Array{Int,2}, weights::Vector{Float64}, vweights:
         @warn "Requested number of clusters larger than unique no. embeddings. Truncating to $unique_rows landmarks."
         land = unique_rows
     end
-    lm = CGE.runsplit(embedding, vweights, clusters, land, forced, method) .+ 1      # landmarks.jl:378-379
+    lm = runsplit_b200(embedding, vweights, clusters, land, forced, method) .+ 1     # landmarks.jl:378-379
     N = Int(maximum(lm)); m = size(edges, 1)
     embed = zeros(dim, N)                       # filled row-major N x dim by the library = dim x N column-major
     lweight = zeros(N); dii = zeros(N); cluster = zeros(Int, N)

@@ -15,6 +15,8 @@ for lib in libcge_b200_x0.so libcge_b200.so; do
   CGE_B200_LIB=$PWD/cge_jl_b200/$lib timeout 300 python scripts/run_config.py --config 3 > gpurun_out/r02_c14_cfg3_$lib.txt 2>&1
   show gpurun_out/r02_c14_cfg3_$lib.txt "cfg3 $lib"
 done
+timeout 600 python -m pytest tests/test_gpu_select.py tests/test_gpu_landmarks.py -m gpu -q > gpurun_out/r02_c14_select_tests.txt 2>&1
+tail -15 gpurun_out/r02_c14_select_tests.txt
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scale.py -m gpu -x -q > gpurun_out/r02_c14_tests.txt 2>&1
 tail -3 gpurun_out/r02_c14_tests.txt
 cp gpurun_out/config_runs.jsonl gpurun_out/r02_c14_config_runs.jsonl

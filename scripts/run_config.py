@@ -34,9 +34,11 @@ EMPTY = (np.zeros(0), np.zeros(0, dtype=np.int64), np.zeros((0, 0), dtype=np.int
          np.zeros((0, 0)))
 
 
-def build(cfg):
+def build(cfg, dev=None):
+    """dev: a Scorer -- landmark selection and aggregation then run on the GPU."""
     t0 = time.perf_counter()
     directed, lm = False, None
+    t_lm = None
     if isinstance(cfg, str):  # "n,d,k,directed" -- ad-hoc synthetic problem (profiling)
         n, d, k, dr = (int(x) for x in cfg.split(","))
         directed = bool(dr)
@@ -47,8 +49,10 @@ def build(cfg):
             by = {}
             for v, c in enumerate(comm[:, 0], start=1):
                 by.setdefault(int(c), []).append(v)
+            t1 = time.perf_counter()
             lm = landmarks(edges, ew, vw, [np.asarray(v) for v in by.values()], comm, emb, False,
-                           LANDMARKS, 4, split_cluster_rss, directed)
+                           LANDMARKS, 4, split_cluster_rss, directed, device=dev)
+            t_lm = time.perf_counter() - t1
             name += f" landmarks -l {LANDMARKS}"
     elif cfg in (1, 2):
         z = np.load(os.path.join(ROOT, "tests", "golden", "example10k.npz"))
@@ -58,8 +62,10 @@ def build(cfg):
             by = {}
             for v, c in enumerate(comm[:, 0], start=1):
                 by.setdefault(int(c), []).append(v)
+            t1 = time.perf_counter()
             lm = landmarks(edges, ew, vw, [np.asarray(v) for v in by.values()], comm, emb, False,
-                           200, 4, split_cluster_rss, False)
+                           200, 4, split_cluster_rss, False, device=dev)
+            t_lm = time.perf_counter() - t1
     elif cfg == 3:
         edges, ew, vw, comm, emb = planted_partition(50000, k=32, d=64, seed=1003, directed=True,
                                                      weighted=True)
@@ -83,12 +89,13 @@ def build(cfg):
             by.setdefault(int(c), []).append(v)
         t1 = time.perf_counter()
         lm = landmarks(edges, ew, vw, [np.asarray(v) for v in by.values()], comm, emb, False,
-                       4000, 4, split_cluster_rss, False)
-        print(f"landmarks(): {time.perf_counter() - t1:.1f} s, N = {lm[1].shape[0]}", flush=True)
+                       4000, 4, split_cluster_rss, False, device=dev)
+        t_lm = time.perf_counter() - t1
+        print(f"landmarks(): {t_lm:.1f} s, N = {lm[1].shape[0]}", flush=True)
     else:
         raise SystemExit("unknown config")
     return dict(edges=edges, ew=ew, vw=vw, comm=comm, emb=emb, directed=directed, lm=lm, name=name,
-                t_gen=time.perf_counter() - t0)
+                t_gen=time.perf_counter() - t0, t_lm=t_lm)
 
 
 def main():
@@ -103,6 +110,8 @@ def main():
     ap.add_argument("--max-alphas", type=int, default=0)
     ap.add_argument("--exact", action="store_true", help="config 5: the exact half (--force-exact)")
     ap.add_argument("--spot", type=int, default=0, help="vertices of the NumPy degree-sum spot check")
+    ap.add_argument("--host-landmarks", action="store_true",
+                    help="landmark mode: runsplit + aggregation in NumPy instead of on the GPU")
     args = ap.parse_args()
     global EXACT
     EXACT = args.exact
@@ -117,7 +126,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     global LANDMARKS
     LANDMARKS = args.landmarks
-    c = build(args.synthetic or args.config)
+    sc = dv.Scorer(local_rank)
+    c = build(args.synthetic or args.config, None if args.host_landmarks else sc)
     n = c["vw"].shape[0]
     t0 = time.perf_counter()
     if c["lm"] is None:
@@ -130,7 +140,6 @@ def main():
         prob = (ledges, lw, lcomm, lemb, dii, lweight, c["vw"], v2l, c["emb"])
         n_scored, target = lemb.shape[0], lweight
     t_sample = time.perf_counter() - t0
-    sc = dv.Scorer(local_rank)
     if world > 1:
         ids = [dv.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
@@ -189,6 +198,7 @@ def main():
         "auc": [float(x) for x in list(st.auc)[: int(st.n_alpha_run)]],
         "matrix_gb_per_gpu": st.matrix_bytes / 1e9,
         "s_run": t_run, "s_upload": t_upload, "s_sampling": t_sample, "s_generate": c["t_gen"],
+        "s_landmarks": c["t_lm"], "landmarks_on": None if c["lm"] is None else ("host" if args.host_landmarks else "gpu"),
         "ms_fp_kernels": float(st.ms_sweeps), "ms_b_kernels": float(st.ms_bsweeps),
         "pair_alphas_per_s": pairs * int(st.n_alpha_run) / t_run,
         "avg_pass_ms": float(st.ms_sweeps) / max(int(st.fp_sweeps), 1),

@@ -42,9 +42,19 @@ def test_device_aggregation_is_bit_identical(scorer, n, k, d, N, directed):
 def test_landmarks_with_device_aggregation_feeds_the_scorer(scorer):
     """landmarks(..., device=scorer) == landmarks(...) on the host, and the scorer's result from the
     device-built landmark graph equals the one from the host-built graph."""
+    import importlib
+    lm_mod = importlib.import_module("cge_jl_b200.landmarks")
     edges, ew, vw, comm, emb = load_fixture("test115.npz")
     args = (edges, ew, vw, clusters_of(comm), comm, emb, False, 20, 1, split_cluster_rss, False)
-    host, dev = landmarks(*args), landmarks(*args, device=scorer)
+    # selection runs on the device as well (SURVEY.md 8(f) F4).  This fixture's clusters (5..14 vertices
+    # in 32 dimensions) have rank-deficient covariances, for which LAPACK's eigenvector SIGN is not stable
+    # under rounding-level differences of the matrix, so both sides use the fixed sign convention here
+    # (tests/test_gpu_select.py compares the LAPACK-callback path)
+    lm_mod.CANONICAL_SIGN, lm_mod.DEVICE_EIG = True, "builtin"
+    try:
+        host, dev = landmarks(*args), landmarks(*args, device=scorer)
+    finally:
+        lm_mod.CANONICAL_SIGN, lm_mod.DEVICE_EIG = False, "lapack"
     for a, b in zip(dev, host):
         assert np.array_equal(a, b)
     dii, lemb, lcomm, ledges, lw, lweight, v2l = dev
