@@ -75,7 +75,7 @@ EXPORTS = [
     "cge_b200_p2p_export", "cge_b200_p2p_import", "cge_b200_measure_fp64_peak",
     "cge_b200_selftest_math", "cge_b200_sample_non_edges", "cge_b200_table_dims",
     "cge_b200_read_table", "cge_b200_measure_fp64_pipes", "cge_b200_landmarks_aggregate",
-    "cge_b200_landmarks_select", "cge_b200_sym_top_eigvec",
+    "cge_b200_landmarks_select", "cge_b200_sym_top_eigvec", "cge_b200_unique_rows",
 ]
 
 _lib = None
@@ -126,6 +126,7 @@ def load():
                                               C.c_int64, _pi, _pi, C.c_int32, C.c_int64, C.c_int64,
                                               C.c_int32, EIGVEC_FN, vp, _pi, _pi]
     lib.cge_b200_sym_top_eigvec.argtypes = [_pd, C.c_int64, _pd, _pd]
+    lib.cge_b200_unique_rows.argtypes = [vp, C.c_int64, C.c_int64, _pd, C.c_int64, C.c_int64, _pi]
     lib.cge_b200_debug_read.argtypes = [vp, C.c_int, _pd, C.c_int64]
     _lib = lib
     return lib

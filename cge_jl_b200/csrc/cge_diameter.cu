@@ -23,7 +23,7 @@
 
 namespace cge {
 
-constexpr int DM_THREADS = 128;
+constexpr int DM_THREADS = 160;  // 4 epilogue warps + the producer warp
 constexpr float DM_PAD_NORM = -1e30f;
 
 // ---- packing: FP64 rows -> BF16 hi/lo in the canonical K-major no-swizzle UMMA layout ----------
@@ -106,12 +106,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// One CTA (128 threads = 4 warps = the 128 TMEM lanes) per SM; strips of tiles of one tile row are
-// claimed from a counter.  Thread 0 is the TMA producer and the MMA issuer; all four warps are the
-// epilogue (thread t owns accumulator row t).  TWO accumulators in TMEM (2 x 128 columns): the 24 MMAs
-// of tile i+1 are issued before the epilogue of tile i starts, so the tensor pipe works through them
-// while the four warps read tile i's accumulator back (tcgen05.ld) and take its maximum.
+// One CTA per SM, warp-specialised: warps 0-3 (128 threads = the 128 TMEM lanes) are the epilogue,
+// lane 0 of warp 4 is the producer -- it claims strips of tiles of one tile row from a counter, brings
+// the operand blocks in by TMA and issues the MMAs.  TWO accumulators in TMEM (2 x 128 columns): the 24
+// MMAs of tile i+1 run on the tensor pipe while the epilogue warps read tile i's accumulator back
+// (tcgen05.ld, one row per thread) and take its maximum.  Hand-offs are mbarriers:
+//   b_full[2]   TMA -> producer      column block of tile i has landed in buffer i & 1
+//   mma_done[2] tcgen05.commit -> epilogue (accumulator i & 1 complete) and -> producer (the column
+//               buffer i & 1 may be refilled)
+//   acc_free[2] epilogue (one arrive per warp) -> producer: accumulator i & 1 has been read
+// Strips are separated by CTA-wide barriers (the row block changes); inside a strip nothing but the
+// four epilogue warps' own named barrier (the tile maximum) synchronises more than it must.
 constexpr uint32_t DM_TMEM_COLS = 256;
+constexpr int DM_EPI_THREADS = 128;
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_constant__ DiamArgs a) {
     extern __shared__ __align__(1024) unsigned char sm[];
     const uint32_t opb = (uint32_t)a.ksteps * 4096u;
@@ -119,14 +127,16 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
     unsigned char *sB = sm + 2 * opb;             // two buffers of (hi, lo)
     float *nA = reinterpret_cast<float *>(sm + 6 * (size_t)opb);
     float *nB = nA + TILE;                        // [2][128]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(nB + 2 * TILE);  // a_full, b_full[2], mma_done[2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 5);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(nB + 2 * TILE);  // a_full, b_full[2], mma_done[2], acc_free[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 7);
     int *s_strip = reinterpret_cast<int *>(tmem_slot + 1);         // bi, bj0, count, first tile
     float *s_red = reinterpret_cast<float *>(s_strip + 4);         // [4]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    uint64_t *a_full = bars, *b_full = bars + 1, *mma_done = bars + 3;
+    uint64_t *a_full = bars, *b_full = bars + 1, *mma_done = bars + 3, *acc_free = bars + 5;
+    const bool producer = tid == DM_EPI_THREADS;  // lane 0 of warp 4
     if (tid == 0) {
         for (int i = 0; i < 5; ++i) mbar_init(bars + i, 1);
+        for (int i = 5; i < 7; ++i) mbar_init(bars + i, 4);  // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -145,11 +155,13 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
     // (N>>3 at [17,23)), M = 128 (M>>4 at [24,29))
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t pol = l2_policy(true);  // blocks are re-read by many CTAs: keep them in L2
-    uint32_t ph_a = 0, ph_b = 0, ph_m = 0;  // ph_b / ph_m: one phase bit per buffer
+    // phase bits, one per buffer.  Producer: ph_a, ph_b (b_full), ph_m (mma_done), ph_f (acc_free);
+    // epilogue threads: ph_m only.
+    uint32_t ph_a = 0, ph_b = 0, ph_m = 0, ph_f = 0;
     float lmax = 0.0f;
     const size_t blk_bytes = 2 * (size_t)opb;
     while (true) {
-        if (tid == 0) {
+        if (producer) {
             const unsigned s = atomicAdd(a.strip_counter, 1u);
             int4 st = make_int4(-1, 0, 0, 0);
             if (s < (unsigned)a.n_strips) st = a.strips[s];
@@ -158,83 +170,100 @@ __global__ void __launch_bounds__(DM_THREADS, 1) k_diameter_filter(const __grid_
         __syncthreads();
         const int bi = s_strip[0], bj0 = s_strip[1], cnt = s_strip[2], t0 = s_strip[3];
         if (bi < 0) break;
-        // thread 0: wait for tile i's column block, issue its MMAs into accumulator i & 1
-        auto issue = [&](int i) {
-            const int buf = i & 1;
-            if (i == 0) {
-                mbar_wait(a_full, ph_a);
-                ph_a ^= 1u;
-            }
-            mbar_wait(b_full + buf, (ph_b >> buf) & 1u);
-            ph_b ^= 1u << buf;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + opb;
-            const uint32_t b_hi = smem_u32(sB + (size_t)buf * blk_bytes), b_lo = b_hi + opb;
-            const uint32_t acc_addr = tmem + (uint32_t)buf * 128u;
-            uint32_t acc = 0;
-            // Gram tile = hi.hi + hi.lo + lo.hi ; K step s covers k-chunks 2s, 2s+1
-            for (int term = 0; term < 3; ++term) {
-                const uint32_t pa = term == 2 ? a_lo : a_hi, pb = term == 1 ? b_lo : b_hi;
-                for (int s = 0; s < a.ksteps; ++s) {
-                    umma_bf16(acc_addr, umma_desc(pa + (uint32_t)s * 4096u, 2048u, 128u),
-                              umma_desc(pb + (uint32_t)s * 4096u, 2048u, 128u), idesc, acc);
-                    acc = 1;
-                }
-            }
-            umma_commit(mma_done + buf);
-        };
-        auto request_b = [&](int i) {  // column block of tile i into buffer i & 1 (its last reader is done)
-            const int buf = i & 1;
-            mbar_expect_tx(b_full + buf, 2 * opb);
-            bulk_g2s(sB + (size_t)buf * blk_bytes, a.packed + (size_t)(bj0 + i) * blk_bytes, 2 * opb,
-                     b_full + buf, pol);
-        };
-        if (tid == 0) {
-            // every MMA of the previous strip has completed (its last mma_done was waited for), so the
-            // row block and both column buffers are free
+        if (producer) {
+            auto request_b = [&](int i) {  // column block of tile i into buffer i & 1
+                const int buf = i & 1;
+                mbar_expect_tx(b_full + buf, 2 * opb);
+                bulk_g2s(sB + (size_t)buf * blk_bytes, a.packed + (size_t)(bj0 + i) * blk_bytes, 2 * opb,
+                         b_full + buf, pol);
+            };
+            // the previous strip is fully drained (barrier at its end): every buffer is free
             mbar_expect_tx(a_full, 2 * opb);
             bulk_g2s(sA, a.packed + (size_t)bi * blk_bytes, 2 * opb, a_full, pol);
             request_b(0);
             if (cnt > 1) request_b(1);
-        }
-        nA[tid] = a.norms[(size_t)bi * TILE + tid];
-        nB[tid] = a.norms[(size_t)bj0 * TILE + tid];
-        __syncthreads();  // also: every thread has read s_strip
-        if (tid == 0) issue(0);
-        for (int i = 0; i < cnt; ++i) {
-            const int buf = i & 1;
-            // the other accumulator was read by the epilogue of tile i-1, which ended at the barrier
-            // below: tile i+1's MMAs may start while this tile's accumulator is read back
-            if (tid == 0 && i + 1 < cnt) issue(i + 1);
-            if (i + 1 < cnt) nB[(buf ^ 1) * TILE + tid] = a.norms[(size_t)(bj0 + i + 1) * TILE + tid];
-            mbar_wait(mma_done + buf, (ph_m >> buf) & 1u);
-            ph_m ^= 1u << buf;
-            // tile i's MMAs are complete: its column buffer can take the block of tile i+2
-            if (tid == 0 && i + 2 < cnt) request_b(i + 2);
-            __syncwarp();  // lane 0 of warp 0 rejoins before the warp-collective TMEM loads
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // epilogue: thread tid owns accumulator row tid (TMEM lane), 128 FP32 columns
-            const float *nb_ = nB + buf * TILE;
-            float best = -3.0e38f;
-#pragma unroll
-            for (int c0 = 0; c0 < TILE; c0 += 32) {
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128 + c0), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) best = fmaxf(best, fmaf(-2.0f, v[j], nb_[c0 + j]));
+            mbar_wait(a_full, ph_a);
+            ph_a ^= 1u;
+            const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + opb;
+            for (int i = 0; i < cnt; ++i) {
+                const int buf = i & 1;
+                if (i >= 2) {  // accumulator i & 1 was last used by tile i-2: wait until it has been read
+                    mbar_wait(acc_free + buf, (ph_f >> buf) & 1u);
+                    ph_f ^= 1u << buf;
+                }
+                mbar_wait(b_full + buf, (ph_b >> buf) & 1u);
+                ph_b ^= 1u << buf;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t b_hi = smem_u32(sB + (size_t)buf * blk_bytes), b_lo = b_hi + opb;
+                const uint32_t acc_addr = tmem + (uint32_t)buf * 128u;
+                uint32_t acc = 0;
+                // Gram tile = hi.hi + hi.lo + lo.hi ; K step s covers k-chunks 2s, 2s+1
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t pa = term == 2 ? a_lo : a_hi, pb = term == 1 ? b_lo : b_hi;
+                    for (int s = 0; s < a.ksteps; ++s) {
+                        umma_bf16(acc_addr, umma_desc(pa + (uint32_t)s * 4096u, 2048u, 128u),
+                                  umma_desc(pb + (uint32_t)s * 4096u, 2048u, 128u), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                umma_commit(mma_done + buf);
+                // tile i-1's MMAs (the last readers of the other column buffer) complete while tile i's
+                // run: refill that buffer with the block of tile i+1
+                if (i >= 1) {
+                    mbar_wait(mma_done + (buf ^ 1), (ph_m >> (buf ^ 1)) & 1u);
+                    ph_m ^= 1u << (buf ^ 1);
+                    if (i + 1 < cnt) request_b(i + 1);
+                }
             }
-            best += nA[tid];
+            // drain: the last tile's completion (keeps the producer's mma_done phases in step) and the
+            // acc_free arrivals of the last two tiles
+            {
+                const int buf = (cnt - 1) & 1;
+                mbar_wait(mma_done + buf, (ph_m >> buf) & 1u);
+                ph_m ^= 1u << buf;
+            }
+            for (int i = cnt < 2 ? 0 : cnt - 2; i < cnt; ++i) {
+                const int buf = i & 1;
+                mbar_wait(acc_free + buf, (ph_f >> buf) & 1u);
+                ph_f ^= 1u << buf;
+            }
+        } else if (tid < DM_EPI_THREADS) {
+            nA[tid] = a.norms[(size_t)bi * TILE + tid];
+            nB[tid] = a.norms[(size_t)bj0 * TILE + tid];
+            epi_bar();
+            for (int i = 0; i < cnt; ++i) {
+                const int buf = i & 1;
+                if (i + 1 < cnt) nB[(buf ^ 1) * TILE + tid] = a.norms[(size_t)(bj0 + i + 1) * TILE + tid];
+                mbar_wait(mma_done + buf, (ph_m >> buf) & 1u);
+                ph_m ^= 1u << buf;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // thread tid owns accumulator row tid (TMEM lane), 128 FP32 columns
+                const float *nb_ = nB + buf * TILE;
+                float best = -3.0e38f;
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, off));
-            if (lane == 0) s_red[warp] = best;
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();  // this accumulator's reads are done before tile i+2's MMAs overwrite it
-            if (tid == 0) {
-                const float m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-                a.tile_max[(size_t)t0 + i] = m;
-                lmax = fmaxf(lmax, m);
+                for (int c0 = 0; c0 < TILE; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 128 + c0), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) best = fmaxf(best, fmaf(-2.0f, v[j], nb_[c0 + j]));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_free + buf);  // this warp's 32 rows have been read
+                best += nA[tid];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) best = fmaxf(best, __shfl_xor_sync(FULL, best, off));
+                if (lane == 0) s_red[warp] = best;
+                epi_bar();  // s_red complete; also orders the nB write above before the next tile's reads
+                if (tid == 0) {
+                    const float m = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+                    a.tile_max[(size_t)t0 + i] = m;
+                    lmax = fmaxf(lmax, m);
+                }
+                epi_bar();  // s_red may be overwritten
             }
         }
+        __syncthreads();  // strip drained: operand buffers, accumulators and s_strip are free
     }
     if (tid == 0) atomicMax(a.gmax_bits, __float_as_uint(fmaxf(lmax, 0.0f)));
     __syncthreads();
@@ -261,7 +290,7 @@ __global__ void k_select_candidates(const float *__restrict__ tile_max, long lon
     }
 }
 
-size_t diameter_smem_bytes(int ksteps) { return 6 * (size_t)ksteps * 4096 + 3 * TILE * 4 + 128; }
+size_t diameter_smem_bytes(int ksteps) { return 6 * (size_t)ksteps * 4096 + 3 * TILE * 4 + 128; }  // 7 barriers + 9 words
 
 void launch_pack_bf16(const double *emb, const double *mean, int dp, int n, int d_true, int nb,
                       unsigned char *packed, float *norms, unsigned *rmax_bits, cudaStream_t st) {

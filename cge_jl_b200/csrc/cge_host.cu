@@ -2048,6 +2048,27 @@ int cge_b200_landmarks_select(cge_b200_handle *h, int64_t n, int64_t d, const do
     return 0;
 }
 
+int cge_b200_unique_rows(cge_b200_handle *h, int64_t n, int64_t d, const double *embed,
+                         int64_t embed_row_stride, int64_t embed_col_stride, int64_t *out_count) {
+    if (!h || n <= 0 || d <= 0 || n >= ((int64_t)1 << 31) || !embed || !out_count)
+        return fail(CGE_B200_ERR_ARG, "bad unique_rows argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    std::vector<double> x;
+    const double *xr = embed;
+    if (!(embed_col_stride == 1 && embed_row_stride == d)) {
+        x.resize((size_t)(n * d));
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = 0; j < d; ++j)
+                x[(size_t)(i * d + j)] = embed[i * embed_row_stride + j * embed_col_stride];
+        xr = x.data();
+    }
+    std::string msg;
+    long long c = 0;
+    if (count_unique_rows_device(h->stream, n, (int)d, xr, &c, msg) != 0) return fail(CGE_B200_ERR_CUDA, msg);
+    *out_count = c;
+    return 0;
+}
+
 int cge_b200_sym_top_eigvec(const double *a, int64_t d, double *v_out, double *lambda) {
     if (!a || !v_out || d <= 0 || d > 4096) return fail(CGE_B200_ERR_ARG, "bad sym_top_eigvec argument");
     sym_top_eigvec(a, (int)d, v_out, lambda);

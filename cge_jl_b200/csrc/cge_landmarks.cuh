@@ -22,6 +22,9 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
                             const int *cl_members, long long land, long long forced, int rule,
                             SelectEigFn eig, void *eig_user, long long *out_group, long long *out_cuts,
                             std::string &msg);
+// landmarks.jl:369 -- size(unique(embedding, dims=1), 1) on the device (host pointer in, count out)
+int count_unique_rows_device(cudaStream_t st, long long n, int d, const double *x_rowmajor,
+                             long long *out_count, std::string &msg);
 // unit-length eigenvector of the largest eigenvalue of a symmetric d x d matrix (upper triangle read),
 // largest-magnitude component positive
 void sym_top_eigvec(const double *a, int d, double *v_out, double *lambda_out);

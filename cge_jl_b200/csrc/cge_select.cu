@@ -216,158 +216,45 @@ __global__ void k_sel_side_keys(const unsigned char *__restrict__ side, long lon
     if (p < len) key[seg_off + p] = side[p];
 }
 
-// ---------------------------------------------------------------------------------------------------
-// host: principal axis of a symmetric d x d matrix (upper triangle given)
-// ---------------------------------------------------------------------------------------------------
-}  // namespace
-
-// Eigenvector of the LARGEST eigenvalue of the symmetric matrix a (row-major d x d, upper triangle
-// read), unit length, largest-magnitude component positive.  Householder tridiagonalisation,
-// bisection on the Sturm sequence for the top eigenvalue, inverse iteration on the tridiagonal
-// matrix, back-transformation.  ~(4/3) d^3 flop.
-void sym_top_eigvec(const double *a_in, int d, double *v_out, double *lambda_out) {
-    std::vector<double> A((size_t)d * d);
-    for (int i = 0; i < d; ++i)
-        for (int j = i; j < d; ++j) A[(size_t)i * d + j] = A[(size_t)j * d + i] = a_in[(size_t)i * d + j];
-    std::vector<double> diag(d), off(std::max(d, 1), 0.0), tau(d, 0.0);
-    // reduce to tridiagonal form T = Q^T A Q with reflectors H_k = I - tau u u^T (u stored in column k
-    // below the subdiagonal, u[k+1] = 1 implied)
-    std::vector<double> u(d), p(d);
-    for (int k = 0; k + 2 < d; ++k) {
-        double sigma = 0.0;
-        for (int i = k + 2; i < d; ++i) sigma += A[(size_t)i * d + k] * A[(size_t)i * d + k];
-        const double alpha = A[(size_t)(k + 1) * d + k];
-        if (sigma == 0.0) {
-            tau[k] = 0.0;
-            continue;
-        }
-        const double nrm = std::sqrt(alpha * alpha + sigma);
-        const double beta = alpha > 0.0 ? -nrm : nrm;
-        const double u0 = alpha - beta;
-        tau[k] = (beta - alpha) / beta;  // = 2 / (u^T u) * u0^2 with u scaled so that u[k+1] = 1
-        for (int i = k + 2; i < d; ++i) A[(size_t)i * d + k] /= u0;
-        A[(size_t)(k + 1) * d + k] = beta;
-        // u = (1, A[k+2..][k]); apply to the trailing block B = A[k+1.., k+1..]: B <- H B H
-        const int m = d - k - 1;
-        u[0] = 1.0;
-        for (int i = 1; i < m; ++i) u[i] = A[(size_t)(k + 1 + i) * d + k];
-        for (int i = 0; i < m; ++i) {
-            double s = 0.0;
-            const double *row = &A[(size_t)(k + 1 + i) * d + (k + 1)];
-            for (int j = 0; j < m; ++j) s += row[j] * u[j];
-            p[i] = tau[k] * s;
-        }
-        double up = 0.0;
-        for (int i = 0; i < m; ++i) up += u[i] * p[i];
-        const double kk = 0.5 * tau[k] * up;
-        for (int i = 0; i < m; ++i) p[i] -= kk * u[i];  // q = p - (tau/2)(u.p) u
-        for (int i = 0; i < m; ++i) {
-            double *row = &A[(size_t)(k + 1 + i) * d + (k + 1)];
-            const double ui = u[i], pi = p[i];
-            for (int j = 0; j < m; ++j) row[j] -= ui * p[j] + pi * u[j];
-        }
+// ---- number of distinct embedding rows (landmarks.jl:369: size(unique(embedding, dims=1), 1)) ----------
+// one warp per row: 64-bit hash of the row's bit patterns (isequal semantics, as Julia's unique)
+__global__ void k_row_hash(const double *__restrict__ x, long long n, int d, unsigned long long *__restrict__ h,
+                           int *__restrict__ id) {
+    const long long r = (long long)blockIdx.x * SEL_TY + threadIdx.y;
+    if (r >= n) return;
+    const unsigned long long *row = reinterpret_cast<const unsigned long long *>(x) + (size_t)r * d;
+    unsigned long long acc = 0x9E3779B97F4A7C15ull * (unsigned long long)(threadIdx.x + 1);
+    for (int j = threadIdx.x; j < d; j += SEL_TX) {
+        unsigned long long v = row[j] + 0x9E3779B97F4A7C15ull * (unsigned long long)(j + 1);
+        v = (v ^ (v >> 30)) * 0xBF58476D1CE4E5B9ull;  // splitmix64 finaliser
+        v = (v ^ (v >> 27)) * 0x94D049BB133111EBull;
+        acc += v ^ (v >> 31);
     }
-    for (int i = 0; i < d; ++i) diag[i] = A[(size_t)i * d + i];
-    for (int i = 0; i + 1 < d; ++i) off[i] = A[(size_t)(i + 1) * d + i];
-    // largest eigenvalue of T by bisection (Sturm count of eigenvalues < x)
-    double lo = diag[0], hi = diag[0];
-    for (int i = 0; i < d; ++i) {
-        const double r = (i > 0 ? std::fabs(off[i - 1]) : 0.0) + (i + 1 < d ? std::fabs(off[i]) : 0.0);
-        lo = std::min(lo, diag[i] - r);
-        hi = std::max(hi, diag[i] + r);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (threadIdx.x == 0) {
+        h[r] = acc;
+        id[r] = (int)r;
     }
-    const double scale = std::max(std::fabs(lo), std::fabs(hi));
-    const double tiny = std::max(scale, 1e-300) * 1e-300 + 1e-300;
-    auto count_below = [&](double xv) {
-        int c = 0;
-        double q = diag[0] - xv;
-        if (q < 0.0) ++c;
-        for (int i = 1; i < d; ++i) {
-            if (q == 0.0) q = tiny;
-            q = diag[i] - xv - off[i - 1] * off[i - 1] / q;
-            if (q < 0.0) ++c;
-        }
-        return c;
-    };
-    for (int it = 0; it < 200; ++it) {
-        const double mid = 0.5 * (lo + hi);
-        if (mid <= lo || mid >= hi) break;
-        if (count_below(mid) >= d) hi = mid; else lo = mid;  // all d eigenvalues below mid -> go down
+}
+// rows sorted by hash: position p starts a new distinct row unless its hash AND its content equal those of
+// p - 1 (one warp per position compares the rows only when the hashes agree)
+__global__ void k_row_distinct(const double *__restrict__ x, long long n, int d,
+                               const unsigned long long *__restrict__ h, const int *__restrict__ id,
+                               unsigned long long *__restrict__ count) {
+    const long long p = (long long)blockIdx.x * SEL_TY + threadIdx.y;
+    if (p >= n) return;
+    bool fresh = p == 0 || h[p] != h[p - 1];
+    if (!fresh) {
+        const unsigned long long *a = reinterpret_cast<const unsigned long long *>(x) + (size_t)id[p] * d;
+        const unsigned long long *b = reinterpret_cast<const unsigned long long *>(x) + (size_t)id[p - 1] * d;
+        bool diff = false;
+        for (int j = threadIdx.x; j < d; j += SEL_TX) diff |= a[j] != b[j];
+        fresh = __any_sync(0xffffffffu, diff);
     }
-    const double lam = 0.5 * (lo + hi);
-    // inverse iteration on T - lam I (tridiagonal LU with partial pivoting)
-    std::vector<double> y(d, 1.0), a1(d), b1(d), c1(d), c2(d);
-    std::vector<char> swp(d, 0);
-    const double eps = 2.220446049250313e-16;
-    const double pert = std::max(scale, 1e-300) * eps;
-    for (int i = 0; i < d; ++i) y[i] = 1.0 + 0.01 * ((i * 7919) % 13);
-    {
-        // factor once
-        for (int i = 0; i < d; ++i) {
-            b1[i] = diag[i] - lam;
-            c1[i] = i + 1 < d ? off[i] : 0.0;
-            c2[i] = 0.0;
-        }
-        for (int i = 0; i + 1 < d; ++i) {
-            const double sub = off[i];
-            if (std::fabs(sub) > std::fabs(b1[i])) {  // swap rows i, i+1
-                swp[i] = 1;
-                const double nb = sub, nc = b1[i + 1], nc2 = c1[i + 1];
-                const double ob = b1[i], oc = c1[i];
-                b1[i] = nb; c1[i] = nc; c2[i] = nc2;
-                const double l = ob / nb;
-                a1[i] = l;
-                b1[i + 1] = oc - l * nc;
-                c1[i + 1] = -l * nc2;
-            } else {
-                if (b1[i] == 0.0) b1[i] = pert;
-                const double l = sub / b1[i];
-                a1[i] = l;
-                b1[i + 1] -= l * c1[i];
-            }
-        }
-        if (b1[d - 1] == 0.0) b1[d - 1] = pert;
-    }
-    for (int iter = 0; iter < 4; ++iter) {
-        for (int i = 0; i + 1 < d; ++i) {  // forward
-            if (swp[i]) std::swap(y[i], y[i + 1]);
-            y[i + 1] -= a1[i] * y[i];
-        }
-        for (int i = d - 1; i >= 0; --i) {  // backward
-            double s = y[i];
-            if (i + 1 < d) s -= c1[i] * y[i + 1];
-            if (i + 2 < d) s -= c2[i] * y[i + 2];
-            y[i] = s / b1[i];
-        }
-        double nrm = 0.0;
-        for (int i = 0; i < d; ++i) nrm = std::max(nrm, std::fabs(y[i]));
-        if (!(nrm > 0.0) || !std::isfinite(nrm)) {
-            for (int i = 0; i < d; ++i) y[i] = i == 0 ? 1.0 : 0.0;
-            break;
-        }
-        for (int i = 0; i < d; ++i) y[i] /= nrm;
-    }
-    // back-transform: v = H_0 H_1 ... H_{d-3} y
-    for (int k = d - 3; k >= 0; --k) {
-        if (tau[k] == 0.0) continue;
-        double s = y[k + 1];
-        for (int i = k + 2; i < d; ++i) s += A[(size_t)i * d + k] * y[i];
-        s *= tau[k];
-        y[k + 1] -= s;
-        for (int i = k + 2; i < d; ++i) y[i] -= s * A[(size_t)i * d + k];
-    }
-    double n2 = 0.0;
-    for (int i = 0; i < d; ++i) n2 += y[i] * y[i];
-    n2 = std::sqrt(n2);
-    int big = 0;
-    for (int i = 1; i < d; ++i)
-        if (std::fabs(y[i]) > std::fabs(y[big])) big = i;
-    const double sgn = y[big] < 0.0 ? -1.0 : 1.0;
-    for (int i = 0; i < d; ++i) v_out[i] = sgn * y[i] / n2;
-    if (lambda_out) *lambda_out = lam;
+    if (fresh && threadIdx.x == 0) atomicAdd(count, 1ull);
 }
 
-namespace {
 
 // ---------------------------------------------------------------------------------------------------
 // host: the reference's queue (landmarks.jl:12-46), entries are segments
@@ -797,6 +684,53 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
     for (size_t g = 0; g < pq.size(); ++g)
         for (long long r = 0; r < pq[g].len; ++r) out_group[h_idx[(size_t)(pq[g].off + r)]] = (long long)g;
     if (out_cuts) *out_cuts = S.n_cuts;
+    return 0;
+}
+
+
+// Number of distinct rows of the row-major n x d matrix (host pointer).  Rows are hashed (64 bits), sorted by
+// hash, and neighbours with equal hashes are compared in full, so the count is exact unless two DIFFERENT
+// rows collide in 64 bits and interleave with duplicates of themselves.  Returns 0 or -1 (CUDA failure).
+int count_unique_rows_device(cudaStream_t st, long long n, int d, const double *x_rowmajor,
+                             long long *out_count, std::string &msg) {
+    double *x = nullptr;
+    unsigned long long *h = nullptr, *h2 = nullptr, *cnt = nullptr;
+    int *id = nullptr, *id2 = nullptr;
+    void *tmp = nullptr;
+    cudaError_t err = cudaSuccess;
+    auto ok = [&](cudaError_t e) {
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+        return err == cudaSuccess;
+    };
+    size_t tb = 0;
+    ok(cudaMalloc(&x, (size_t)n * d * 8));
+    ok(cudaMalloc(&h, (size_t)n * 8));
+    ok(cudaMalloc(&h2, (size_t)n * 8));
+    ok(cudaMalloc(&id, (size_t)n * 4));
+    ok(cudaMalloc(&id2, (size_t)n * 4));
+    ok(cudaMalloc(&cnt, 8));
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, h, h2, id, id2, (int)n, 0, 64, st);
+    ok(cudaMalloc(&tmp, std::max<size_t>(tb, 1)));
+    unsigned long long c = 0;
+    if (err == cudaSuccess) {
+        ok(cudaMemcpyAsync(x, x_rowmajor, (size_t)n * d * 8, cudaMemcpyHostToDevice, st));
+        ok(cudaMemsetAsync(cnt, 0, 8, st));
+        const unsigned blocks = (unsigned)((n + SEL_TY - 1) / SEL_TY);
+        k_row_hash<<<blocks, dim3(SEL_TX, SEL_TY), 0, st>>>(x, n, d, h, id);
+        ok(cub::DeviceRadixSort::SortPairs(tmp, tb, h, h2, id, id2, (int)n, 0, 64, st));
+        k_row_distinct<<<blocks, dim3(SEL_TX, SEL_TY), 0, st>>>(x, n, d, h2, id2, cnt);
+        ok(cudaMemcpyAsync(&c, cnt, 8, cudaMemcpyDeviceToHost, st));
+        ok(cudaStreamSynchronize(st));
+        ok(cudaGetLastError());
+    }
+    for (void *p : {(void *)x, (void *)h, (void *)h2, (void *)id, (void *)id2, (void *)cnt, tmp})
+        if (p) cudaFree(p);
+    if (err != cudaSuccess) {
+        msg = std::string("unique rows: ") + cudaGetErrorString(err);
+        cudaGetLastError();
+        return -1;
+    }
+    *out_count = (long long)c;
     return 0;
 }
 

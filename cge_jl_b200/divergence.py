@@ -239,6 +239,16 @@ class Scorer:
         return (dii, embed, cluster.reshape(-1, 1), np.stack([oa[:k], ob[:k]], axis=1), ow[:k].copy(),
                 lweight)
 
+    def unique_rows(self, embedding):
+        """``cge_b200_unique_rows``: ``size(unique(embedding, dims=1), 1)`` (landmarks.jl:369) on the
+        device."""
+        em = np.asarray(embedding, dtype=np.float64)
+        n, d = em.shape
+        out = C.c_int64()
+        _check(self._lib.cge_b200_unique_rows(self._h, n, d, _pd(em), em.strides[0] // 8, em.strides[1] // 8,
+                                              C.byref(out)))
+        return out.value
+
     def landmarks_select(self, embedding, vweights, clusters, land, forced, rule, eig="lapack"):
         """``cge_b200_landmarks_select``: ``runsplit`` (landmarks.jl:279-345) with
         the cuts of the split rule on the device.  ``clusters``: list of 1-based vertex-id arrays

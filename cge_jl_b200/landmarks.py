@@ -6,6 +6,7 @@ in this image.  All vertex / landmark ids handled here are 1-based like the refe
 """
 from __future__ import annotations
 
+import os
 import sys
 
 import numpy as np
@@ -83,7 +84,7 @@ CANONICAL_SIGN = False
 # who answers the d x d eigenproblem of a cut when the selection runs on the device (landmarks(..., device=)):
 # "lapack" = numpy.linalg.eigh through the library's callback (this mirror's own routine), "builtin" = the
 # library's solver with the canonical sign
-DEVICE_EIG = "lapack"
+DEVICE_EIG = os.environ.get("CGE_B200_EIG", "lapack")
 
 
 def _pc1(m, w):
@@ -265,7 +266,8 @@ def landmarks(edges, weights, vweights, clusters, comm, embedding, verbose, land
     if verbose:
         print("Starts landmark generation")
     rows_embed, dim = embedding.shape
-    unique_rows = np.unique(embedding, axis=0).shape[0]
+    unique_rows = (device.unique_rows(embedding) if device is not None
+                   else np.unique(embedding, axis=0).shape[0])
     if land > unique_rows:
         print(f"Warning: Requested number of clusters larger than unique no. embeddings. "
               f"Truncating to {unique_rows} landmarks.", file=sys.stderr)

@@ -270,6 +270,12 @@ int cge_b200_landmarks_select(cge_b200_handle *h, int64_t n, int64_t d, const do
                               int32_t index_base, int64_t land, int64_t forced, int32_t rule,
                               cge_b200_eigvec_fn eig, void *eig_user, int64_t *out_group, int64_t *out_cuts);
 
+/* landmarks.jl:369 -- size(unique(embedding, dims=1), 1), the row count landmarks() caps `land` with
+ * (:371-374), on the device: rows are hashed, sorted by hash, and neighbours with equal hashes compared in
+ * full (bit patterns: isequal semantics, like Julia's unique).  5 s of hashing on the host at 10^6 x 128. */
+int cge_b200_unique_rows(cge_b200_handle *h, int64_t n, int64_t d, const double *embed,
+                         int64_t embed_row_stride, int64_t embed_col_stride, int64_t *out_count);
+
 /* Host-only helper of the above, exported for its unit test: unit-length eigenvector of the largest
  * eigenvalue of the symmetric d x d matrix a (row-major, upper triangle read), largest-magnitude component
  * positive; *lambda (optional) receives the eigenvalue. */

@@ -171,6 +171,22 @@ end
 const RULE_CODES = Dict{Function,Int32}(CGE.split_cluster_rss => 0, CGE.split_cluster_size => 2,
                                         CGE.split_cluster_diameter => 3)
 
+# size(unique(embedding, dims=1), 1) (landmarks.jl:369) on the device: cge_b200_unique_rows
+function unique_rows_b200(embedding::Array{Float64,2})
+    rows, dim = size(embedding)
+    out = Ref{Int64}(0)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:cge_b200_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), 0, h))
+    try
+        GC.@preserve embedding check(ccall((:cge_b200_unique_rows, LIB), Cint,
+                                           (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Int64, Ref{Int64}),
+                                           h[], rows, dim, embedding, 1, rows, out))
+    finally
+        ccall((:cge_b200_destroy, LIB), Cvoid, (Ptr{Cvoid},), h[])
+    end
+    return Int(out[])
+end
+
 """
     runsplit_b200(embedding, w, initial_clusters, n, s, rule)
 
@@ -218,7 +234,7 @@ function landmarks_b200(edges::Array{Int,2}, weights::Vector{Float64}, vweights:
                         clusters::Vector{Vector{Int}}, comm::Array{Int,2}, embedding::Array{Float64,2},
                         verbose::Bool, land::Int, forced::Int, method::Function, directed::Bool)
     rows_embed, dim = size(embedding)
-    unique_rows = size(unique(embedding, dims=1), 1)
+    unique_rows = unique_rows_b200(embedding)                                    # landmarks.jl:369
     if land > unique_rows
         @warn "Requested number of clusters larger than unique no. embeddings. Truncating to $unique_rows landmarks."
         land = unique_rows

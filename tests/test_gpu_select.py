@@ -46,7 +46,7 @@ def test_device_selection_equals_the_host_mirror(scorer, n, k, d, land, forced, 
     # the host's LAPACK through the callback: the mirror's own eigenvectors, signs included
     group, cuts = scorer.landmarks_select(emb, vw, clusters, land, forced, rule, eig="lapack")
     ref = _mirror(emb, vw, clusters, land, forced, rule, canonical=False)
-    assert group.min() == 0 and group.max() == land - 1 and cuts >= 1
+    assert group.min() == 0 and group.max() + 1 >= land and cuts >= 1  # (forced cuts can exceed land)
     if k == 0 and not np.array_equal(group, ref):
         # The 115-vertex fixture has clusters of 5..14 vertices in 32 dimensions: rank-deficient
         # covariances, for which the SIGN LAPACK returns flips with rounding-level differences of the
@@ -123,3 +123,17 @@ def test_readme_golden_through_the_device_selection(scorer):
                   False, samples=samples, scorer=scorer)
     assert out[0] == 6.25
     assert abs(out[1] - 0.002961243353776198) <= 1e-9 * 0.002961243353776198
+
+
+def test_unique_rows_matches_numpy(scorer):
+    """cge_b200_unique_rows == size(unique(embedding, dims=1), 1) (landmarks.jl:369)."""
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(50000, 24))
+    x[rng.integers(0, 50000, size=7000)] = x[rng.integers(0, 50000, size=7000)]  # duplicates, some chained
+    x[100:140] = 0.0
+    x[7] = x[8] = np.nan  # Julia's unique (isequal) counts equal NaN rows once; np.unique does not
+    ref = np.unique(x[~np.isnan(x).any(axis=1)], axis=0).shape[0] + 1
+    assert scorer.unique_rows(x) == ref
+    assert scorer.unique_rows(np.asfortranarray(x)) == ref
+    assert scorer.unique_rows(np.ones((300, 5))) == 1
+    assert scorer.unique_rows(rng.normal(size=(1, 3))) == 1
