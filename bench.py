@@ -259,7 +259,7 @@ def secondary_config2(dv, local_rank):
     for _ in range(3):
         sc.upload(problem, keep)
         sc.run()
-    ts, te, sweeps, sweep_ms = [], [], 0, 0.0
+    ts, te, sweeps, sweep_ms = [], [], 0, 0.0  # (k_fixed_point launches only: without the fused first passes)
     for _ in range(5):
         t0 = time.perf_counter()
         sc.upload(problem, keep)
@@ -268,8 +268,8 @@ def secondary_config2(dv, local_rank):
         t2 = time.perf_counter()
         ts.append(t2 - t1)
         te.append(t2 - t0)
-        sweeps += st.fp_sweeps
-        sweep_ms += st.ms_sweeps
+        sweeps += st.fp_sweeps - st.b_fused
+        sweep_ms += st.ms_sweeps - st.ms_fused
     sc.close()
     a = int(st.n_alpha_run)
     # the first call of a FRESH process (kernel modules not loaded yet, CUDA's default lazy loading):
@@ -374,7 +374,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     dt_e2e = dt_res = 0.0
-    ev_ms, sweep_ms, sweeps, launches, bs_ms, b_alone = [], 0.0, 0, 0, 0.0, 0
+    ev_ms, sweep_ms, sweeps, launches, bs_ms, b_alone, fused_ms, fused = [], 0.0, 0, 0, 0.0, 0, 0.0, 0
     out = st = None
     for _ in range(steps):
         whole, resident, out, st = step()
@@ -384,6 +384,8 @@ def run_b200(args):
         sweep_ms += st.ms_sweeps
         bs_ms += st.ms_bsweeps
         b_alone += int(st.b_sweeps) - int(st.b_fused)
+        fused_ms += float(st.ms_fused)
+        fused += int(st.b_fused)
         sweeps += st.fp_sweeps
         launches += st.launches
     sampler.stop_flag = True
@@ -405,11 +407,15 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     # dominant kernel: the fixed point.  Persistent drivers: one launch per alpha runs all its
     # passes; host loop: one launch per pass.  Algorithmic bytes = 8 B per unordered pair and pass.
+    # The first pass of an alpha whose predecessor's B sweep was deferred runs in k_bfp<M> (B sweep + pass in
+    # one matrix read); those launches are timed separately (stats.ms_fused) and reported as `fused_pass`,
+    # so the roofline below is the fixed-point kernel's own launches and the passes they executed.
     persistent = int(stats.driver) in (2, 3)
     fp_launches = (a_run if persistent else int(stats.fp_sweeps)) * steps
-    passes_per_launch = sweeps / max(fp_launches, 1)
+    fp_passes = sweeps - fused
+    passes_per_launch = fp_passes / max(fp_launches, 1)
     bytes_per_launch = 8.0 * pairs / world * passes_per_launch
-    avg_launch_s = 1e-3 * sweep_ms / max(fp_launches, 1)
+    avg_launch_s = 1e-3 * (sweep_ms - fused_ms) / max(fp_launches, 1)
     achieved = bytes_per_launch / avg_launch_s / 1e9 if avg_launch_s > 0 else 0.0
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum from the committed ncu capture of this workload
@@ -425,8 +431,8 @@ def run_b200(args):
     if not stored:
         kname = {1: "k_sweep_rc<false>", 2: "k_fixed_point_rc<false>", 3: "k_fixed_point_rc<false>"}
     elif int(stats.b_fused) > 0:
-        kname[2] = ("k_fixed_point<M,false> (all passes of one alpha per cooperative launch; the first pass of "
-                    "an alpha runs in k_bfp<M> together with the previous alpha's B sweep and is timed with it)")
+        kname[2] = ("k_fixed_point<M,false> (all passes of one alpha per cooperative launch but the first, which "
+                    "k_bfp<M> runs together with the previous alpha's B sweep: see fused_pass)")
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
         "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt_res / steps,
@@ -466,12 +472,17 @@ def run_b200(args):
                      "launches_timed": int(fp_launches),
                      "b_sweep_gbs": 8.0 * pairs / world * b_alone / (bs_ms * 1e-3) / 1e9
                                     if bs_ms > 0 and b_alone > 0 else None,
+                     "fused_pass": None if fused == 0 else {
+                         "kernel": "k_bfp<M> (B sweep of alpha-1/4 + first fixed-point pass of alpha, one matrix read)",
+                         "launches_timed": int(fused), "avg_launch_us": 1e3 * fused_ms / fused,
+                         "gbs": 8.0 * pairs / world * fused / (fused_ms * 1e-3) / 1e9,
+                         "frac": 8.0 * pairs / world * fused / (fused_ms * 1e-3) / 1e9 / peak if peak else None,
+                         "note": "8 B x unordered pairs credited ONCE per launch although it does the work of two sweeps"},
                      "note": "achieved = 8 B x unordered pairs x passes in the launch / CUDA-event "
                              "duration of the launch, events recorded by the library on its stream; per GPU. "
                              "The B sweep of an alpha rides on the first fixed-point pass of the next alpha "
-                             "(k_bfp: one matrix read for both); those kernels are timed with the fixed-point "
-                             "launches, their extra work is NOT credited as bytes; b_sweep_gbs covers the "
-                             "stand-alone B sweeps only",
+                             "(k_bfp: one matrix read for both): those launches and the pass they carry are "
+                             "reported under fused_pass, not here; b_sweep_gbs covers the stand-alone B sweeps",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)"
                                     if "hbm_gbs" in peaks else "fallback 6650 GB/s"},
     }

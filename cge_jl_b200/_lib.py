@@ -52,7 +52,7 @@ class Stats(C.Structure):
         ("n_ranks", C.c_int32), ("regime", C.c_int32), ("diam_candidate_tiles", C.c_int32),
         ("ms_upload", C.c_float), ("ms_build", C.c_float), ("ms_solve", C.c_float),
         ("ms_total", C.c_float), ("ms_sweeps", C.c_float), ("ms_bsweeps", C.c_float),
-        ("b_fused", C.c_int32), ("reserved", C.c_int32),
+        ("b_fused", C.c_int32), ("ms_fused", C.c_float),
     ]
 
     def as_dict(self):

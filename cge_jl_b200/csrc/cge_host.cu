@@ -1387,8 +1387,15 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     // converged T, and so does the first fixed-point pass of alpha m+1 (T is warm-started), so when
     // alpha m+1 is certain to run, B of alpha m is computed by k_bfp<m+1> together with that pass
     // and its score is booked one iteration late -- same numbers, one matrix read less per alpha.
+    // Each k_bfp<m> is one more kernel for CUDA to load on first use (~10 ms per instantiation in a fresh
+    // process), more than the sweeps it saves on a small problem, so by default the sweep is deferred only
+    // when a rank's share of the matrix is at least 1 GiB (a rank-independent test: every rank must take the
+    // same path).  CGE_B200_FUSE_B=1 / 0 forces it on / off.
     bool can_fuse = stored && !small && !h->directed && driver == CGE_B200_DRIVER_PERSISTENT;
-    if (const char *e = getenv("CGE_B200_FUSE_B")) can_fuse = can_fuse && atoi(e) != 0;
+    if (const char *e = getenv("CGE_B200_FUSE_B"))
+        can_fuse = can_fuse && atoi(e) != 0;
+    else
+        can_fuse = can_fuse && h->n_tiles * (int64_t)TILE_ELEMS * 8 / std::max(h->n_ranks, 1) >= ((int64_t)1 << 30);
     int pending_b = 0;  // exponent whose B rides on the next alpha's first pass (0: none)
     char *pin = static_cast<char *>(h->pinned);
     double *pin_auc = reinterpret_cast<double *>(pin + 64);
@@ -1452,7 +1459,7 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
                 cudaEventRecord(h->next_event(), st);
                 launch_tiles(m, 4, grid, st, A);  // B of m-1 + pass 1 of m
                 cudaEventRecord(h->next_event(), st);
-                h->ev_is_b.push_back(0);  // carries a fixed-point pass: booked with the sweeps
+                h->ev_is_b.push_back(2);  // carries a fixed-point pass: booked with the sweeps (and ms_fused)
                 ++h->launches;
             }
             ++S.b_sweeps;
@@ -1633,7 +1640,8 @@ static int do_run(cge_b200_handle *h, double *out, int32_t *out_len, cge_b200_st
     for (size_t i = 0; i < h->ev_is_b.size(); ++i) {
         float ms = 0.f;  // pool entries 0..2 are the phase markers, sweep pairs follow
         if (cudaEventElapsedTime(&ms, h->evpool[3 + 2 * i], h->evpool[4 + 2 * i]) == cudaSuccess)
-            (h->ev_is_b[i] ? S.ms_bsweeps : S.ms_sweeps) += ms;
+            (h->ev_is_b[i] == 1 ? S.ms_bsweeps : S.ms_sweeps) += ms;
+        if (h->ev_is_b[i] == 2) S.ms_fused += ms;
     }
     {
         unsigned long long lh[4];

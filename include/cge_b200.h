@@ -138,9 +138,9 @@ typedef struct cge_b200_stats {
     float ms_sweeps;                        /* sum of the fixed-point sweep kernels (CUDA events) */
     float ms_bsweeps;                       /* sum of the stand-alone B sweep kernels (CUDA events) */
     int32_t b_fused;                        /* of b_sweeps: B sweeps that rode on the first fixed-point
-                                               pass of the next alpha (one matrix read for both; their
-                                               kernel time is part of ms_sweeps) */
-    int32_t reserved;
+                                               pass of the next alpha (one matrix read for both; that
+                                               pass is counted in fp_sweeps, its kernel time in ms_sweeps) */
+    float ms_fused;                         /* of ms_sweeps: the fused B + first-pass kernels (k_bfp) */
 } cge_b200_stats;
 
 typedef struct cge_b200_handle cge_b200_handle;

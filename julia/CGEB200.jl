@@ -54,10 +54,10 @@ mutable struct Stats
     n_tiles::Int32; grid::Int32; driver::Int32; n_ranks::Int32; regime::Int32; diam_candidate_tiles::Int32
     ms_upload::Float32; ms_build::Float32; ms_solve::Float32; ms_total::Float32
     ms_sweeps::Float32; ms_bsweeps::Float32
-    b_fused::Int32; reserved::Int32
+    b_fused::Int32; ms_fused::Float32
     Stats() = new(0, 0, ntuple(_ -> Int32(0), N_ALPHA), ntuple(_ -> NaN, N_ALPHA),
                   ntuple(_ -> NaN, N_ALPHA), 0.0, 0.0, 0.0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                  0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0, 0)
+                  0f0, 0f0, 0f0, 0f0, 0f0, 0f0, 0, 0f0)
 end
 
 last_error() = unsafe_string(ccall((:cge_b200_last_error, LIB), Cstring, ()))

@@ -375,6 +375,32 @@ def test_column_major_embedding_is_accepted_without_copy(scorer):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("split", [False, True])
+def test_deferred_b_sweep_is_the_same_computation(scorer, split, monkeypatch):
+    """The B sweep of alpha fused into the first fixed-point pass of alpha + 1/4 (k_bfp): identical passes
+    and T bit for bit (the degree-sum arithmetic is tile_pass_u's), per-alpha global scores equal to the
+    B atomics' 1e-13, oracle parity -- on a problem whose patience counters switch the local score off
+    early, so deferred, stand-alone and skipped B sweeps all occur."""
+    n = 900
+    edges, ew, vw, comm, emb = planted_partition(n, 6, 16, seed=41, weighted=True)
+    samples = dv.draw_samples(edges, ew, n, 800, 42, False, True)
+    monkeypatch.setenv("CGE_B200_RT_EXPONENT", "0")  # the per-alpha kernels, as on large problems
+    runs = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("CGE_B200_FUSE_B", fuse)
+        out, st = dv.wGCL(edges, ew, comm, emb, np.zeros(n), vw, *EMPTY, split, 42, 800, False,
+                          samples=samples, return_stats=True, scorer=scorer, driver=2, regime=1)
+        runs[fuse] = (out, st, scorer.debug_read(1, n))
+    (a, sa, ta), (b, sb, tb) = runs["0"], runs["1"]
+    assert sa.b_fused == 0 and sb.b_fused >= 5 and sb.b_sweeps == sa.b_sweeps
+    assert list(sa.iters) == list(sb.iters) and np.array_equal(ta, tb)
+    assert np.array_equal(a[4:], b[4:]) and a[0] == b[0]
+    np.testing.assert_allclose(b, a, rtol=1e-12)
+    np.testing.assert_allclose(np.array(list(sb.div)), np.array(list(sa.div)), rtol=1e-12, equal_nan=True)
+    ref, tr = oracle.wgcl(edges, ew, comm, emb, np.zeros(n), vw, samples=samples, split=split)
+    assert_parity(b, sb, ref, tr)
+
+
 def test_run_is_bit_reproducible(scorer):
     """Fixed reduction orders everywhere in the fixed point: repeated runs agree bit for bit on
     everything that does not pass through the B atomics, and to 1e-13 on the global score."""
