@@ -324,7 +324,8 @@ struct Sel {
     size_t tmp_bytes = 0;
     int sm_count = 148, max_mblk = 0, max_cblk = 0;
     // host
-    std::vector<double> h_fin, h_cov, h_z, h_zs;
+    // pinned, so that the many small device -> host reads of a cut are real asynchronous copies
+    double *h_fin = nullptr, *h_cov = nullptr, *h_z = nullptr;  // [2 (1+2d)], [dp dp], [n] (z or sorted z)
     cudaError_t err = cudaSuccess;
     std::string msg;
     long long n_cuts = 0;
@@ -342,6 +343,8 @@ struct Sel {
                         (void *)fin, (void *)covp, (void *)idx, (void *)idx2, (void *)pos, (void *)perm,
                         (void *)rank, (void *)key, (void *)key2, (void *)side, tmp})
             if (p) cudaFree(p);
+        for (void *p : {(void *)h_fin, (void *)h_cov, (void *)h_z})
+            if (p) cudaFreeHost(p);
     }
 
     int mom_blocks(long long len) const {
@@ -355,8 +358,7 @@ struct Sel {
         k_sel_moments<<<dim3(nblk, nranges), dim3(SEL_TX, SEL_TY), smem, st>>>(x, w, idx, via, seg_off, r0,
                                                                                r1, d, part);
         k_sel_sum_blocks<<<(comps * nranges + 127) / 128, 128, 0, st>>>(part, nblk, comps, nranges, fin);
-        h_fin.resize((size_t)2 * comps);
-        if (!ok(cudaMemcpyAsync(h_fin.data(), fin, (size_t)nranges * comps * 8, cudaMemcpyDeviceToHost, st)))
+        if (!ok(cudaMemcpyAsync(h_fin, fin, (size_t)nranges * comps * 8, cudaMemcpyDeviceToHost, st)))
             return false;
         return ok(cudaStreamSynchronize(st));
     }
@@ -411,6 +413,9 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
     S.alloc(S.key, (size_t)n);
     S.alloc(S.key2, (size_t)n);
     S.alloc(S.side, (size_t)n);
+    S.ok(cudaMallocHost(reinterpret_cast<void **>(&S.h_fin), (size_t)2 * comps * 8));
+    S.ok(cudaMallocHost(reinterpret_cast<void **>(&S.h_cov), (size_t)S.dp * S.dp * 8));
+    S.ok(cudaMallocHost(reinterpret_cast<void **>(&S.h_z), (size_t)n * 8));
     {
         size_t b1 = 0, b2 = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, b1, S.z, S.zs, S.pos, S.perm, (int)n, 0, 64, st);
@@ -440,7 +445,7 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
             return true;
         }
         if (!S.moments(off, nullptr, Range{0, len}, Range{0, 0}, 1)) return false;
-        e.mom.assign(S.h_fin.begin(), S.h_fin.begin() + comps);
+        e.mom.assign(S.h_fin, S.h_fin + comps);
         e.value = -total_of(e.mom.data(), d);
         return true;
     };
@@ -462,8 +467,7 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
         k_sel_cov<<<cblk, COV_THREADS, cov_smem, st>>>(S.x, S.w, S.idx, off, len, S.mu, d, S.dp, S.covp);
         double *cfin = S.covp + (size_t)S.max_cblk * S.dp * S.dp;
         k_sel_sum_blocks<<<(S.dp * S.dp + 127) / 128, 128, 0, st>>>(S.covp, cblk, S.dp * S.dp, 1, cfin);
-        S.h_cov.resize((size_t)S.dp * S.dp);
-        S.ok(cudaMemcpyAsync(S.h_cov.data(), cfin, (size_t)S.dp * S.dp * 8, cudaMemcpyDeviceToHost, st));
+        S.ok(cudaMemcpyAsync(S.h_cov, cfin, (size_t)S.dp * S.dp * 8, cudaMemcpyDeviceToHost, st));
         if (!S.ok(cudaStreamSynchronize(st))) return -1;
         std::vector<double> C((size_t)d * d), v(d);
         for (int i = 0; i < d; ++i)
@@ -487,10 +491,9 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
             S.ok(cub::DeviceRadixSort::SortPairs(S.tmp, tb, S.z + off, S.zs + off, S.pos + off, S.perm + off,
                                                  (int)len, 0, 64, st));
             k_sel_invert<<<lblocks, 256, 0, st>>>(S.perm, off, len, S.rank);
-            S.h_zs.resize((size_t)len);
-            S.ok(cudaMemcpyAsync(S.h_zs.data(), S.zs + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st));
+            S.ok(cudaMemcpyAsync(S.h_z, S.zs + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st));
             if (!S.ok(cudaStreamSynchronize(st))) return -1;
-            const double *zs = S.h_zs.data();
+            const double *zs = S.h_z;
             if (!(zs[0] < zs[len - 1])) {
                 msg = "Trying to split homogenous cluster";  // :165-167
                 return -2;
@@ -514,8 +517,8 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
                 // zs values in that range are all equal: nothing to rotate
             }
             if (!S.moments(off, S.perm, Range{0, 1}, Range{len - 1, 1}, 2)) return -1;
-            std::vector<double> rss_low(S.h_fin.begin(), S.h_fin.begin() + comps);
-            std::vector<double> rss_high(S.h_fin.begin() + comps, S.h_fin.begin() + 2 * comps);
+            std::vector<double> rss_low(S.h_fin, S.h_fin + comps);
+            std::vector<double> rss_high(S.h_fin + comps, S.h_fin + 2 * comps);
             long long lo = 1, hi = len - 1;  // gray = ranks [lo, hi)
             // accepted ranges in acceptance order
             std::vector<Range> acc_low, acc_high;
@@ -529,8 +532,8 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
                     const long long p = std::lower_bound(zs + lo, zs + hi, med) - zs;  // first z >= med
                     if (!S.moments(off, S.perm, Range{lo, p - lo}, Range{p, hi - p}, 2)) return -1;
                     std::vector<double> low_tmp = rss_low, high_tmp = rss_high;
-                    add_to(low_tmp, S.h_fin.data());
-                    add_to(high_tmp, S.h_fin.data() + comps);
+                    add_to(low_tmp, S.h_fin);
+                    add_to(high_tmp, S.h_fin + comps);
                     if (total_of(low_tmp.data(), d) < total_of(high_tmp.data(), d)) {
                         if (p == lo) break;
                         rss_low.swap(low_tmp);
@@ -550,8 +553,8 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
             if (hi > lo) {  // :199-207
                 if (!S.moments(off, S.perm, Range{lo, hi - lo}, Range{0, 0}, 1)) return -1;
                 std::vector<double> low_tmp = rss_low, high_tmp = rss_high;
-                add_to(low_tmp, S.h_fin.data());
-                add_to(high_tmp, S.h_fin.data());
+                add_to(low_tmp, S.h_fin);
+                add_to(high_tmp, S.h_fin);
                 gray_low = std::max(total_of(low_tmp.data(), d), total_of(rss_high.data(), d)) <
                            std::max(total_of(rss_low.data(), d), total_of(high_tmp.data(), d));
             }
@@ -582,10 +585,9 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
         } else {
             // ---- split_cluster_size (:218-238) / split_cluster_diameter (:247-267): threshold on z, ties
             // alternate by the running lengths in member order ----
-            S.h_z.resize((size_t)len);
-            S.ok(cudaMemcpyAsync(S.h_z.data(), S.z + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st));
+            S.ok(cudaMemcpyAsync(S.h_z, S.z + off, (size_t)len * 8, cudaMemcpyDeviceToHost, st));
             if (!S.ok(cudaStreamSynchronize(st))) return -1;
-            const double *z = S.h_z.data();
+            const double *z = S.h_z;
             double thr;
             if (rule == 2) {
                 std::vector<double> t(z, z + len);
@@ -634,9 +636,22 @@ int landmarks_select_device(int device, cudaStream_t st, long long n, int d, con
             msg = "Unexpected empty cluster generated";
             return -2;
         }
+        // both children's moments (-> their queue values and, later, their means) in one launch
         Entry lowc, highc;
-        if (!make_entry(e.off, cut, lowc)) return -1;
-        if (!make_entry(e.off + cut, e.len - cut, highc)) return -1;
+        lowc.off = e.off; lowc.len = cut;
+        highc.off = e.off + cut; highc.len = e.len - cut;
+        lowc.value = highc.value = eps;  // singletons go to the tail of the queue (:311, :319)
+        if (lowc.len > 1 || highc.len > 1) {
+            if (!S.moments(e.off, nullptr, Range{0, lowc.len}, Range{cut, highc.len}, 2)) return -1;
+            if (lowc.len > 1) {
+                lowc.mom.assign(S.h_fin, S.h_fin + comps);
+                lowc.value = -total_of(lowc.mom.data(), d);
+            }
+            if (highc.len > 1) {
+                highc.mom.assign(S.h_fin + comps, S.h_fin + 2 * comps);
+                highc.value = -total_of(highc.mom.data(), d);
+            }
+        }
         heap_put(pq, std::move(lowc));
         heap_put(pq, std::move(highc));
         return 0;

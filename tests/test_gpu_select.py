@@ -137,3 +137,24 @@ def test_unique_rows_matches_numpy(scorer):
     assert scorer.unique_rows(np.asfortranarray(x)) == ref
     assert scorer.unique_rows(np.ones((300, 5))) == 1
     assert scorer.unique_rows(rng.normal(size=(1, 3))) == 1
+
+
+@pytest.mark.parametrize("method", [split_cluster_rss, split_cluster_size, split_cluster_diameter])
+def test_reference_landmark_assertions_on_the_device_path(scorer, method):
+    """What the reference's own tests assert about landmarks() (test/runtests.jl:43-95: array types, 1-based
+    edge ids, one community column), for the device path on the reference's test graph, plus the structural
+    facts the scorer relies on."""
+    edges, ew, vw, comm, emb = load_fixture("test115.npz")
+    dii, lemb, lcomm, ledges, lw, lweight, v2l = landmarks(edges, ew, vw, clusters_of(comm), comm, emb, False,
+                                                           25, 2, method, False, device=scorer)
+    assert ledges.dtype == np.int64 and ledges.ndim == 2 and ledges.min() == 1
+    assert lw.dtype == np.float64 and lw.ndim == 1 and lw.shape[0] == ledges.shape[0]
+    assert lcomm.dtype == np.int64 and lcomm.shape[1] == 1
+    assert dii.dtype == np.float64 and dii.ndim == 1
+    N = lemb.shape[0]
+    assert N >= 25 and dii.shape[0] == N and lcomm.shape[0] == N and ledges.max() <= N
+    assert v2l.min() == 1 and v2l.max() == N and np.unique(v2l).size == N  # every landmark has a member
+    assert np.isclose(lweight.sum(), vw.sum()) and np.isclose(lw.sum(), ew.sum())
+    # a landmark never mixes communities' clusters: its members share the initial cluster
+    for L in range(1, N + 1):
+        assert np.unique(comm[v2l == L, 0]).size == 1

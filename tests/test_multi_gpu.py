@@ -28,10 +28,12 @@ def _problem(directed):
     return n, edges, ew, vw, comm, emb
 
 
-def _worker(rank, world, port, directed, p2p, regime, q):
+def _worker(rank, world, port, directed, p2p, regime, q, fuse=False):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    if fuse:  # per-alpha kernels and the deferred B sweep (k_bfp), as on large problems
+        os.environ.update(CGE_B200_RT_EXPONENT="0", CGE_B200_FUSE_B="1")
     if regime == 2:
         os.environ["CGE_B200_RC_SB"] = "2"  # super-tiles of 2 x 2 tiles: 21 work units over the ranks
     torch.cuda.set_device(rank)
@@ -55,7 +57,7 @@ def _worker(rank, world, port, directed, p2p, regime, q):
     dist.barrier()
     if rank == 0:
         q.put((out, list(st.iters), list(st.div), list(st.auc), int(st.n_ranks), int(st.driver),
-               int(st.regime)))
+               int(st.regime), int(st.b_fused)))
     sc.close()
     dist.destroy_process_group()
 
@@ -90,7 +92,7 @@ def test_sharded_matches_one_gpu_and_oracle(world, directed, p2p, regime):
              for r in range(world)]
     for p in procs:
         p.start()
-    out2, iters2, div2, auc2, n_ranks, driver, reg = q.get(timeout=600)
+    out2, iters2, div2, auc2, n_ranks, driver, reg, _ = q.get(timeout=600)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -139,3 +141,48 @@ def test_single_process_two_gpus(directed, regime, driver):
     assert out1[0] == out2[0] and out1[4] == out2[4]
     np.testing.assert_allclose(out2, out1, rtol=RTOL, atol=1e-15)
     del keep
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_deferred_b_sweep(world, monkeypatch):
+    """The B sweep of an alpha riding on the first pass of the next one (k_bfp) with the tiles sharded over
+    `world` ranks: every rank fills its own partial slots and its own B in the fused launch, the persistent
+    kernel starts at the exchange, B is all-reduced one alpha late.  Same passes, same scores as one GPU
+    without the fusion; and the same through cge_b200_score_multi (threads of one process, B summed on the
+    host)."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+
+    from cge_jl_b200 import divergence as dv
+    from util import RTOL, empty_landmark_args
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, False, True, 1, q, True)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out2, iters2, div2, auc2, n_ranks, driver, reg, fused = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert n_ranks == world and driver == 2 and reg == 1 and fused >= 5
+    n, edges, ew, vw, comm, emb = _problem(False)
+    samples = dv.draw_samples(edges, ew, n, 2000, 42, False, True)
+    out1, st1 = dv.wGCL(edges, ew, comm, emb, np.zeros(n), vw, *empty_landmark_args(), False, 42, 2000,
+                        False, samples=samples, return_stats=True)
+    assert st1.b_fused == 0 and list(st1.iters) == iters2
+    assert out1[0] == out2[0] and out1[4] == out2[4]
+    np.testing.assert_allclose(out2, out1, rtol=RTOL, atol=1e-15)
+    np.testing.assert_allclose(np.array(div2), np.array(list(st1.div)), rtol=RTOL, equal_nan=True)
+    if world == 2:
+        monkeypatch.setenv("CGE_B200_RT_EXPONENT", "0")
+        monkeypatch.setenv("CGE_B200_FUSE_B", "1")
+        p, keep = dv.make_problem(edges, ew, comm, emb, np.zeros(n), vw, None, None, None, False, False,
+                                  samples, 0, 0, 1)
+        out3, st3 = dv.score_multi(p, 2)
+        assert st3.b_fused >= 5 and list(st3.iters) == iters2
+        np.testing.assert_allclose(out3, out1, rtol=RTOL, atol=1e-15)
+        del keep
