@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace cge {
 
 constexpr int TILE = 128;
@@ -232,6 +234,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 // fixed-point pass, undirected (divergence.jl:152-159)
 // warp w owns rows 16w..16w+15 of the tile, lane l owns columns 2l, 2l+1, 64+2l, 65+2l
 // ---------------------------------------------------------------------------------------------
+#ifndef CGE_ROWRED4
+#define CGE_ROWRED4 1
+#endif
+// CGE_ROWRED4: the 16 row sums of a warp are reduced across the lanes four at a time (warp_treduce<4> per
+// batch of four rows) instead of all at once (warp_treduce<16>).  Every row's sum runs through the same
+// tree either way -- partners lane ^ 16, ^ 8, ^ 4, ^ 2, ^ 1 in that order, and a + b == b + a -- so the
+// partial slots are bit-identical; what changes is that only 4 row sums are live at a time, which leaves
+// the compiler room to keep more of a tile's 32 loads in flight under the 128-register cap.  Measured
+// (r02, same box, config 4): 27.33 -> 26.79 ms per pass (0.894 -> 0.912 of the HBM peak); 10k example
+// 69.7 -> 68.1 us.
 template <int M>
 __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int bi, int bj,
                                             const SweepArgs &a, double *s_col, uint64_t pol) {
@@ -243,8 +255,31 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
     const double trow =
         lane < ROWS_PER_WARP ? __ldcg(a.Ta + (size_t)bi * TILE + row0 + lane) : 0.0;
     const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
-    double racc[ROWS_PER_WARP];
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+#if CGE_ROWRED4
+#pragma unroll
+    for (int batch = 0; batch < ROWS_PER_WARP / 4; ++batch) {
+        double r4[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int rr = batch * 4 + r;
+            const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
+            const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
+            const double ti = __shfl_sync(FULL, trow, rr);
+            const double g0 = powm_any<M>(v01.x, a.m), g1 = powm_any<M>(v01.y, a.m);
+            const double g2 = powm_any<M>(v23.x, a.m), g3 = powm_any<M>(v23.y, a.m);
+            r4[r] = fma(g3, tc23.y, fma(g2, tc23.x, fma(g1, tc01.y, g0 * tc01.x)));
+            c0 = fma(ti, g0, c0);
+            c1 = fma(ti, g1, c1);
+            c2 = fma(ti, g2, c2);
+            c3 = fma(ti, g3, c3);
+        }
+        warp_treduce<4>(r4, lane);
+        if ((lane & 7) == 0)
+            a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + batch * 4 + treduce_index<4>(lane)] = r4[0];
+    }
+#else
+    double racc[ROWS_PER_WARP];
 #pragma unroll
     for (int rr = 0; rr < ROWS_PER_WARP; ++rr) {
         const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
@@ -261,6 +296,7 @@ __device__ __forceinline__ void tile_pass_u(const double *__restrict__ qt, int b
     warp_treduce<ROWS_PER_WARP>(racc, lane);
     if ((lane & 1) == 0)
         a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + treduce_index<16>(lane)] = racc[0];
+#endif
     const bool offdiag = bi != bj;
     if (offdiag) {
         double2 *sc = reinterpret_cast<double2 *>(s_col + w * TILE);
@@ -303,7 +339,8 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
     double ci0 = 0.0, ci1 = 0.0, ci2 = 0.0, ci3 = 0.0;  // Sin column sums  (Tout_r * g)
     double co0 = 0.0, co1 = 0.0, co2 = 0.0, co3 = 0.0;  // Sout column sums (Tin_r * g)
     // four batches of four rows, the loads of the next batch issued before the current one is
-    // consumed (register double buffering, as in tile_bpass)
+    // consumed (register double buffering, as in tile_bpass).  Leaving the loads to the compiler inside
+    // the row loop, which is what tile_pass_u does, measured the same (r02, config 3: 1.885 -> 1.875 ms).
     constexpr int BR = 4, NBAT = ROWS_PER_WARP / BR;
     double2 v01[2][BR], v23[2][BR];
 #pragma unroll
@@ -327,8 +364,9 @@ __device__ __forceinline__ void tile_pass_d(const double *__restrict__ qt, int b
             const int rr = batch * BR + r4;
             const double t_in = __shfl_sync(FULL, trow_in, rr);
             const double t_out = __shfl_sync(FULL, trow_out, rr);
-            const double g0 = powm_any<M>(v01[cb][r4].x, a.m), g1 = powm_any<M>(v01[cb][r4].y, a.m);
-            const double g2 = powm_any<M>(v23[cb][r4].x, a.m), g3 = powm_any<M>(v23[cb][r4].y, a.m);
+            const double2 q01 = v01[cb][r4], q23 = v23[cb][r4];
+            const double g0 = powm_any<M>(q01.x, a.m), g1 = powm_any<M>(q01.y, a.m);
+            const double g2 = powm_any<M>(q23.x, a.m), g3 = powm_any<M>(q23.y, a.m);
             rin[r4] = fma(g3, to23.y, fma(g2, to23.x, fma(g1, to01.y, g0 * to01.x)));
             rout[r4] = fma(g3, ti23.y, fma(g2, ti23.x, fma(g1, ti01.y, g0 * ti01.x)));
             ci0 = fma(t_out, g0, ci0);
@@ -507,9 +545,6 @@ __device__ __forceinline__ void tile_bpass(const double *__restrict__ qt, int bi
 // tile_pass_u's operation for operation (same FMA chains, same reduction trees: bit-identical
 // partial slots), the bin arithmetic is tile_bpass<M-1>'s.
 // ---------------------------------------------------------------------------------------------
-#ifndef CGE_UB_ROWS
-#define CGE_UB_ROWS 4  // rows requested together in the fused pass (measured r02, config 4: 4 -> 29.31 s per run, 8 -> 29.36, 16 -> 29.74)
-#endif
 template <int M>
 __device__ __forceinline__ void tile_pass_ub(const double *__restrict__ qt, int bi, int bj,
                                              const SweepArgs &a, double *s_col, uint64_t pol) {
@@ -527,7 +562,6 @@ __device__ __forceinline__ void tile_pass_ub(const double *__restrict__ qt, int 
     const int crow = ld ? __ldcg(a.comm + grow) : -1;
     const bool diag = bi == bj;
     const double2 *base = reinterpret_cast<const double2 *>(qt + (size_t)row0 * TILE);
-    double racc[ROWS_PER_WARP];
     double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
     double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;  // bins: sum_r T_r q^(M-1) per column
     int cur = __shfl_sync(FULL, crow, 0);
@@ -542,56 +576,60 @@ __device__ __forceinline__ void tile_pass_ub(const double *__restrict__ qt, int 
         }
         b0 = b1 = b2 = b3 = 0.0;
     };
-
-    constexpr int BR = CGE_UB_ROWS, NB = ROWS_PER_WARP / BR;
+    // The 16 rows of a warp almost always share one community (vertices are sorted by community), and then
+    // the row loop has no branch in it -- the loads of the whole tile can be scheduled ahead, as in
+    // tile_pass_u; a warp whose rows straddle a community boundary takes the same loop with the per-row
+    // check.  Row sums are reduced four rows at a time (see CGE_ROWRED4: bit-identical to tile_pass_u).
+    auto rows = [&](auto check_tag) {
+        constexpr bool CHECK = decltype(check_tag)::value;
 #pragma unroll
-    for (int batch = 0; batch < NB; ++batch) {
-        double2 v01[BR], v23[BR];
+        for (int batch = 0; batch < ROWS_PER_WARP / 4; ++batch) {
+            double r4[4];
 #pragma unroll
-        for (int r = 0; r < BR; ++r) {
-            v01[r] = ld_stream(base + (batch * BR + r) * (TILE / 2) + lane, pol);
-            v23[r] = ld_stream(base + (batch * BR + r) * (TILE / 2) + 32 + lane, pol);
-        }
-        const unsigned bm = ((1u << BR) - 1u) << (batch * BR);
-        const bool uniform = (__ballot_sync(FULL, crow != cur) & bm) == 0u;
-#pragma unroll
-        for (int r = 0; r < BR; ++r) {
-            const int rr = batch * BR + r;
-            if (!uniform) {
-                const int cr = __shfl_sync(FULL, crow, rr);
-                if (cr != cur) {  // warp-uniform
-                    flush(cur);
-                    cur = cr;
+            for (int r = 0; r < 4; ++r) {
+                const int rr = batch * 4 + r;
+                if constexpr (CHECK) {
+                    const int cr = __shfl_sync(FULL, crow, rr);
+                    if (cr != cur) {  // warp-uniform
+                        flush(cur);
+                        cur = cr;
+                    }
                 }
+                const double2 v01 = ld_stream(base + rr * (TILE / 2) + lane, pol);
+                const double2 v23 = ld_stream(base + rr * (TILE / 2) + 32 + lane, pol);
+                const double q0 = v01.x, q1 = v01.y, q2 = v23.x, q3 = v23.y;
+                const double ti = __shfl_sync(FULL, trow, rr);
+                // fixed-point pass, exponent M (as tile_pass_u)
+                const double g0 = powm<M>(q0), g1 = powm<M>(q1), g2 = powm<M>(q2), g3 = powm<M>(q3);
+                r4[r] = fma(g3, tc23.y, fma(g2, tc23.x, fma(g1, tc01.y, g0 * tc01.x)));
+                c0 = fma(ti, g0, c0);
+                c1 = fma(ti, g1, c1);
+                c2 = fma(ti, g2, c2);
+                c3 = fma(ti, g3, c3);
+                // community bins, exponent M-1 (as tile_bpass<M-1, false>)
+                double h0 = powm<M - 1>(q0), h1 = powm<M - 1>(q1), h2 = powm<M - 1>(q2), h3 = powm<M - 1>(q3);
+                if (diag) {  // unordered pairs once: keep col >= row (divergence.jl:229-230)
+                    const int gr = bi * TILE + row0 + rr;
+                    h0 = gc0 >= gr ? h0 : 0.0;
+                    h1 = gc0 + 1 >= gr ? h1 : 0.0;
+                    h2 = gc2 >= gr ? h2 : 0.0;
+                    h3 = gc2 + 1 >= gr ? h3 : 0.0;
+                }
+                b0 = fma(ti, h0, b0);
+                b1 = fma(ti, h1, b1);
+                b2 = fma(ti, h2, b2);
+                b3 = fma(ti, h3, b3);
             }
-            const double q0 = v01[r].x, q1 = v01[r].y, q2 = v23[r].x, q3 = v23[r].y;
-            const double ti = __shfl_sync(FULL, trow, rr);
-            // fixed-point pass, exponent M (as tile_pass_u)
-            const double g0 = powm<M>(q0), g1 = powm<M>(q1), g2 = powm<M>(q2), g3 = powm<M>(q3);
-            racc[rr] = fma(g3, tc23.y, fma(g2, tc23.x, fma(g1, tc01.y, g0 * tc01.x)));
-            c0 = fma(ti, g0, c0);
-            c1 = fma(ti, g1, c1);
-            c2 = fma(ti, g2, c2);
-            c3 = fma(ti, g3, c3);
-            // community bins, exponent M-1 (as tile_bpass<M-1, false>)
-            double h0 = powm<M - 1>(q0), h1 = powm<M - 1>(q1), h2 = powm<M - 1>(q2), h3 = powm<M - 1>(q3);
-            if (diag) {  // unordered pairs once: keep col >= row (divergence.jl:229-230)
-                const int gr = bi * TILE + row0 + rr;
-                h0 = gc0 >= gr ? h0 : 0.0;
-                h1 = gc0 + 1 >= gr ? h1 : 0.0;
-                h2 = gc2 >= gr ? h2 : 0.0;
-                h3 = gc2 + 1 >= gr ? h3 : 0.0;
-            }
-            b0 = fma(ti, h0, b0);
-            b1 = fma(ti, h1, b1);
-            b2 = fma(ti, h2, b2);
-            b3 = fma(ti, h3, b3);
+            warp_treduce<4>(r4, lane);
+            if ((lane & 7) == 0)
+                a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + batch * 4 + treduce_index<4>(lane)] = r4[0];
         }
-    }
+    };
+    if ((__ballot_sync(FULL, crow != cur) & 0xffffu) == 0u)  // lanes 0..15 hold the rows' communities
+        rows(std::false_type{});
+    else
+        rows(std::true_type{});
     flush(cur);
-    warp_treduce<ROWS_PER_WARP>(racc, lane);
-    if ((lane & 1) == 0)
-        a.partA[(size_t)bj * a.np + (size_t)bi * TILE + row0 + treduce_index<16>(lane)] = racc[0];
     if (!diag) {
         double2 *sc = reinterpret_cast<double2 *>(s_col + w * TILE);
         sc[lane] = make_double2(c0, c1);
