@@ -27,6 +27,7 @@ def main():
             m = re.search(r"Function : (\S+)", line)
             if m:
                 name = subprocess.run(["c++filt", m.group(1)], capture_output=True, text=True).stdout.strip()
+                name = name.replace("(anonymous namespace)::", "")
                 name = re.sub(r"\(.*", "", name).replace("void ", "").replace("cge::", "")
                 counts[name] = collections.Counter()
                 continue
@@ -42,7 +43,7 @@ def main():
         for k, c in counts.items():
             if not any(c.values()):
                 continue
-            if os.path.basename(obj) == "cge_inst0.o" and not re.search(r"<1,|<\(int\)1,", k):
+            if os.path.basename(obj) == "cge_inst0.o" and not re.search(r"<1,|<\(int\)1,|k_bfp<2>", k):
                 continue  # one exponent is enough
             if shown == 0:
                 print(f"## {os.path.basename(obj)}")
