@@ -22,7 +22,8 @@ using StatsBase
 using Random
 using LinearAlgebra: eigvecs
 
-export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table, landmarks_b200
+export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table, landmarks_b200, runsplit_b200,
+       unique_rows_b200
 
 const LIB = get(ENV, "CGE_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "cge_jl_b200", "libcge_b200.so")))
@@ -161,7 +162,8 @@ end
 function _principal_axis(c::Ptr{Float64}, d::Int64, v::Ptr{Float64}, ::Ptr{Cvoid})::Cint
     try
         A = unsafe_wrap(Array, c, (Int(d), Int(d)))
-        unsafe_copyto!(v, pointer(eigvecs(Matrix(A))[:, end]), Int(d))    # same call, same LAPACK, same sign
+        axis = eigvecs(Matrix(A))[:, end]                                 # same call, same LAPACK, same sign
+        GC.@preserve axis unsafe_copyto!(v, pointer(axis), Int(d))
         return Cint(0)
     catch
         return Cint(1)
