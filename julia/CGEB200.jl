@@ -17,7 +17,7 @@
 module CGEB200
 
 using CGE
-using CGE: parseargs, landmarks, louvain_clust   # re-exported unchanged; wGCL* are defined here
+using CGE: parseargs, louvain_clust   # re-exported unchanged; wGCL*, landmarks are defined here
 using StatsBase
 using Random
 using LinearAlgebra: eigvecs
@@ -268,6 +268,11 @@ function landmarks_b200(edges::Array{Int,2}, weights::Vector{Float64}, vweights:
     k = Int(n_e[])
     return dii, permutedims(embed), reshape(cluster, :, 1), hcat(oa[1:k], ob[1:k]), ow[1:k], lweight, lm
 end
+
+# `landmarks` as the CLI script calls it (example/CGE_CLI.jl:15-16): on the device (selection and aggregation),
+# or the reference's own function with ENV["CGE_B200_HOST_LANDMARKS"] = "1"
+landmarks(args...) = get(ENV, "CGE_B200_HOST_LANDMARKS", "0") == "1" ? CGE.landmarks(args...) :
+                                                                       landmarks_b200(args...)
 
 function score(directed::Bool, edges, eweights, comm, embed, distances, vweights, init_vweights,
                v_to_l, init_edges, init_eweights, init_embed, split, seed, auc_samples, verbose)
