@@ -28,6 +28,14 @@ export parseargs, landmarks, louvain_clust, wGCL, wGCL_directed, read_table, lan
 const LIB = get(ENV, "CGE_B200_LIB",
                 normpath(joinpath(@__DIR__, "..", "cge_jl_b200", "libcge_b200.so")))
 const N_ALPHA = 40
+
+# One-shot hosts (one scoring call per process, like CGE_CLI.jl): the library holds one kernel instantiation per
+# alpha and CUDA's default lazy loading charges ~10 ms for each on first use (0.40 s for the first call on the 10k
+# example, 0.08 s with eager loading).  Has to be set before the first CUDA call of the process; a caller's own
+# setting wins.
+function __init__()
+    haskey(ENV, "CUDA_MODULE_LOADING") || (ENV["CUDA_MODULE_LOADING"] = "EAGER")
+end
 # above this many vertices NE (n^2/2 tuples + two Sets, divergence.jl:121-137) no longer fits in
 # host memory; non-edges are then drawn on the device (same distribution, different RNG stream)
 const NE_MATERIALIZE_LIMIT = 30_000
